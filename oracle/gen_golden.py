@@ -1,0 +1,168 @@
+"""Generate tests/golden/*.pt by running the REAL reference (askerlee/segtran @ /root/reference).
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container:  python -m oracle.gen_golden
+Each fixture holds seeded inputs, the reference module's state_dict (backbone weights dropped),
+the reference outputs, and the gradients of ``loss = (out * G).sum()`` w.r.t. inputs and
+parameters.  The fixtures pin oracle/segtran_oracle.py (CPU tests) and the CUDA path (GPU tests);
+they are deliberately small (tens to hundreds of KB).
+"""
+from __future__ import annotations
+
+import os
+import sys
+from argparse import Namespace
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_import as R                      # noqa: E402
+from oracle import segtran_oracle as O                  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _grads(module, loss, inputs):
+    params = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+    gs = torch.autograd.grad(loss, [p for _, p in params] + list(inputs), allow_unused=True)
+    gp = {n: g for (n, _), g in zip(params, gs[:len(params)]) if g is not None}
+    gi = list(gs[len(params):])
+    return gp, gi
+
+
+def gen_encoder(name, dims, M, A, pd, qkb, grid, B, seed, wscale=1.0, mask_p=0.2):
+    ns = R.load()
+    cfg = R.encoder_config(ns.shared, dims=dims, num_modes=M, num_attractors=A, pos_dim=pd, qk_have_bias=qkb)
+    enc = R.build_encoder(cfg, seed=seed).eval()
+    if wscale != 1.0:                       # push the scores past attn_clip=500 (segtran_shared.py:578-580)
+        with torch.no_grad():
+            for n, p in enc.named_parameters():
+                if n.endswith("query.weight"):
+                    p.mul_(wscale)
+    N = 1
+    for g in grid:
+        N *= g
+    torch.manual_seed(seed + 100)
+    x = torch.randn(B, N, dims[0], requires_grad=True)
+    pos = O.voxels_pos_for_grid(grid, (8,) * pd, B)
+    mask = (torch.rand(B, N, 1) > mask_p).long()
+    G = torch.randn(B, N, dims[-1])
+    with R.quiet():
+        y = enc(x, pos, mask, torch.Size(grid))
+    gp, gi = _grads(enc, (y * G).sum(), [x])
+    max_attn = [float(t.in_ator_trans.max_attn) for t in enc.translayers] + \
+               [float(t.ator_out_trans.max_attn) for t in enc.translayers]
+    fx = dict(kind="encoder", dims=list(dims), num_modes=M, num_attractors=A, pos_dim=pd, qk_have_bias=qkb,
+              grid=list(grid), x=x.detach(), voxels_pos=pos, vmask=mask, G=G, out=y.detach(),
+              state_dict={k: v.clone() for k, v in enc.state_dict().items()},
+              grad_params=gp, grad_x=gi[0], max_attn=max_attn)
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print(name, "out", tuple(y.shape), "max|out|", float(y.abs().max()), "max_attn", max_attn)
+
+
+class FixedFeatBackbone3d(torch.nn.Module):
+    """Stands in for InceptionI3d.extract_features (aj_i3d.py:325-333): returns stored feature maps."""
+
+    def __init__(self, feats):
+        super().__init__()
+        self.feats = feats
+
+    def extract_features(self, x):
+        keys = ["MaxPool3d_2a_3x3", "Conv3d_2c_3x3", "Mixed_3c", "Mixed_4f", "Mixed_5c"]
+        return dict(zip(keys, self.feats))
+
+
+def gen_seg3d(name, seed=3):
+    ns = R.load()
+    ns.shared.bb2feat_dims["i3d-tiny"] = [8, 16, 24, 32, 48]
+    args = Namespace(num_classes=4, backbone_type="i3d-tiny", use_pretrained=False, num_attractors=12,
+                     num_translayers=1, num_modes=4, trans_output_type="private", mid_type="shared",
+                     orig_in_channels=4, D_pool_K=2, inchan_to3_scheme="bridgeconv", D_groupsize=1, device="cpu",
+                     in_fpn_layers="34", out_fpn_layers="1234", in_fpn_scheme="AN", out_fpn_scheme="AN",
+                     translayer_compress_ratios=[1, 1], dropout_prob=0.0, tie_qk_scheme="shared",
+                     qk_have_bias=True, use_squeezed_transformer=True, pos_code_type="lsinu")
+    torch.manual_seed(seed)
+    with R.quiet():
+        ns.seg3d.CONFIG.update_config(args)
+        net = ns.seg3d.Segtran3d(ns.seg3d.CONFIG)
+    net.eval()
+    B, S = 2, 32
+    c = ns.shared.bb2feat_dims["i3d-tiny"]
+    torch.manual_seed(seed + 1)
+    batch = torch.randn(B, 4, S, S, S)
+    batch[:, :, :, :, :8] = 0                                  # a zero slab (mask is still all-ones in 3-D)
+    feats = [torch.randn(B, c[0], 16, 16, 16), torch.randn(B, c[1], 16, 16, 16), torch.randn(B, c[2], 16, 8, 8),
+             torch.randn(B, c[3], 8, 4, 4), torch.randn(B, c[4], 4, 2, 2)]
+    feats = [f.requires_grad_(True) for f in feats]
+    net.backbone = FixedFeatBackbone3d(feats)
+    G = torch.randn(B, 4, S, S, S)
+    with R.quiet(), R.cuda_literal_to_cpu():
+        y = net(batch)
+    gp, gi = _grads(net, (y * G).sum(), feats[1:])
+    sd = {k: v.clone() for k, v in net.state_dict().items() if not k.startswith("backbone.")}
+    fx = dict(kind="seg3d", args=vars(args), bb_feat_dims=c, batch=batch, feats=[f.detach() for f in feats], G=G,
+              out=y.detach(), state_dict=sd, grad_params=gp, grad_feats=[None] + gi)
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print(name, "out", tuple(y.shape), "max|out|", float(y.abs().max()))
+
+
+class FixedFeatBackbone2d(torch.nn.Module):
+    """Stands in for ResNet.ext_features (resnet.py:186-200)."""
+
+    def __init__(self, feats):
+        super().__init__()
+        self.feats = feats
+
+    def ext_features(self, x):
+        return tuple(self.feats)
+
+
+def gen_seg2d(name, seed=4):
+    ns = R.load()
+    ns.shared.bb2feat_dims["resnet-tiny"] = [8, 16, 24, 32, 48]
+    args = Namespace(num_classes=3, backbone_type="resnet-tiny", use_pretrained=False, num_attractors=10,
+                     num_translayers=2, num_modes=4, trans_output_type="private", mid_type="shared",
+                     device="cpu", in_fpn_layers="34", out_fpn_layers="1234", in_fpn_scheme="AN",
+                     out_fpn_scheme="AN", translayer_compress_ratios=[1, 1, 2], dropout_prob=0.0,
+                     tie_qk_scheme="shared", qk_have_bias=False, use_squeezed_transformer=True,
+                     pos_code_type="lsinu", use_global_bias=False, num_modalities=0)
+    import resnet as ref_resnet
+    ref_resnet.__dict__["resnet-tiny"] = lambda pretrained=False, do_pool1=True: torch.nn.Identity()
+    torch.manual_seed(seed)
+    with R.quiet():
+        ns.seg2d.CONFIG.update_config(args)
+        net = ns.seg2d.Segtran2d(ns.seg2d.CONFIG)
+    net.eval()
+    B, S = 2, 64
+    c = ns.shared.bb2feat_dims["resnet-tiny"]
+    torch.manual_seed(seed + 1)
+    batch = torch.randn(B, 3, S, S)
+    batch[:, :, :16, :] = 0                                    # true zero padding -> masked tokens (segtran2d.py:339)
+    feats = [torch.randn(B, c[0], 32, 32), torch.randn(B, c[1], 32, 32), torch.randn(B, c[2], 16, 16),
+             torch.randn(B, c[3], 8, 8), torch.randn(B, c[4], 4, 4)]
+    feats = [f.requires_grad_(True) for f in feats]
+    net.backbone = FixedFeatBackbone2d(feats)
+    G = torch.randn(B, 3, S, S)
+    with R.quiet():
+        y = net(batch)
+    gp, gi = _grads(net, (y * G).sum(), feats[1:])
+    sd = {k: v.clone() for k, v in net.state_dict().items() if not k.startswith("backbone.")}
+    fx = dict(kind="seg2d", args=vars(args), bb_feat_dims=c, batch=batch, feats=[f.detach() for f in feats], G=G,
+              out=y.detach(), state_dict=sd, grad_params=gp, grad_feats=[None] + gi)
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print(name, "out", tuple(y.shape), "max|out|", float(y.abs().max()))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(4)
+    gen_encoder("enc3d_small", [64, 64], 4, 16, 3, True, (3, 4, 5), 2, seed=1)
+    gen_encoder("enc2d_compress", [64, 64, 32], 4, 8, 2, False, (6, 7), 2, seed=2)
+    gen_encoder("enc3d_clamp", [64, 64], 4, 16, 3, True, (3, 4, 5), 1, seed=7, wscale=60.0)
+    gen_encoder("enc3d_ragged", [96, 96], 4, 24, 3, True, (5, 3, 7), 3, seed=9)       # N=105: not a tile multiple
+    gen_seg3d("seg3d_tiny")
+    gen_seg2d("seg2d_tiny")
+
+
+if __name__ == "__main__":
+    main()
