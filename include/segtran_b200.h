@@ -1,0 +1,183 @@
+/*
+ * segtran_b200 — C ABI of the B200-native Squeeze-and-Expansion hot path.
+ *
+ * The reference (askerlee/segtran) is pure Python/PyTorch and has no FFI layer: the drop-in
+ * boundary is the nn.Module contract of code/networks/segtran_shared.py (SegtranFusionEncoder
+ * :819-975 and the modules it owns) and of the Segtran2d/Segtran3d shells.  This header is the
+ * C ABI introduced *underneath* that contract: every entry point names the
+ * reference call sites whose arithmetic it replaces.  Host binding: ctypes (segtran_b200/_lib.py);
+ * see INTEGRATION.md for the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a caller-owned DEVICE pointer (tensor.data_ptr()); nothing is retained
+ *    after the call returns; scratch is passed in explicitly by the caller;
+ *  - every call is asynchronous on the cudaStream_t given (passed as void*);
+ *  - return 0 on success, negative on error; sx_last_error() returns a thread-local message;
+ *  - no global mutable state apart from one-time function-attribute setup (thread safe: the
+ *    autograd engine calls backward entry points from its own worker thread);
+ *  - the device is the current CUDA context's device (torch sets it); never assumed to be 0.
+ *  - there is NO CPU fallback: a missing GPU / non-sm_100 device is an error.
+ */
+#ifndef SEGTRAN_B200_H_
+#define SEGTRAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SX_VERSION 1
+
+/* element types */
+enum { SX_F32 = 0, SX_BF16 = 1 };
+/* GEMM operand arithmetic: TF32 (fp32 storage, 10-bit mantissa in the tensor core) or BF16 */
+enum { SX_OP_TF32 = 0, SX_OP_BF16 = 1 };
+/* operand majorness: K-major = reduction dim contiguous; MN-major = row/col dim contiguous */
+enum { SX_MAJOR_K = 0, SX_MAJOR_MN = 1 };
+enum { SX_BIAS_NONE = 0, SX_BIAS_N = 1, SX_BIAS_M = 2 };
+enum { SX_ACT_NONE = 0, SX_ACT_GELU = 1 };
+
+int sx_version(void);
+const char* sx_last_error(void);
+/* number of SMs / compute capability of the current device (diagnostics; fails if no GPU) */
+int sx_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched GEMM on tcgen05 tensor cores (TMA-staged operands, fp32 accumulators in TMEM):
+ *     C[z1][z0][m][n] = epilogue( alpha * sum_k A[z1][z0][m][k] * B[z1][z0][n][k] )
+ * Replaces every dense contraction on the path: the Q/K/V projections (segtran_shared.py:559-560,
+ * :414), Q.K^T (:566), P.V (:447), MMSharedMid's shared Linear (:243), MMPrivateOutput's grouped
+ * Conv1d (:267), and all of their backward products.
+ * An operand with majorness K stores element (r,k) at ptr[r*ld + k]; majorness MN at ptr[k*ld + r].
+ * stride_z0/stride_z1 are in elements; 0 broadcasts the operand over that batch dim.
+ * Requirements: ptr 16-byte aligned; ld*elsize and z strides*elsize multiples of 16 bytes.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* ptr;
+  int32_t major;
+  int32_t _pad;
+  int64_t ld;
+  int64_t stride_z0;
+  int64_t stride_z1;
+} sx_operand;
+
+typedef struct {
+  int32_t op_dtype;              /* SX_OP_TF32 | SX_OP_BF16 (A and B element type: f32 | bf16) */
+  int32_t M, N, K, Z0, Z1;
+  sx_operand A, B;
+  void* C;
+  int32_t c_dtype;               /* SX_F32 | SX_BF16 */
+  int32_t round_tf32;            /* round fp32 outputs to TF32 (RN) so a following TF32 GEMM is exact on them */
+  int64_t ldc, c_stride_z0, c_stride_z1;
+  float alpha;
+  int32_t bias_mode;             /* SX_BIAS_* ; bias is fp32 */
+  const float* bias;
+  int64_t bias_stride_z0, bias_stride_z1;
+  int32_t act;                   /* SX_ACT_* */
+  int32_t accumulate;            /* 0: store, 1: atomicAdd into fp32 C (needed when split_k > 1) */
+  void* preact;                  /* optional: pre-activation (after bias) in C's layout and dtype */
+  int32_t split_k;               /* >= 1 */
+  int32_t _pad2;
+  float* amax;                   /* optional: atomicMax of the stored values (attention-score diagnostics, :569-573) */
+  float drop_p;                  /* dropout on the stored value (after act); 0 disables */
+  uint32_t _pad3;
+  uint64_t drop_seed;            /* counter-based mask: keep(idx) = hash(seed, flat index in C) >= p */
+} sx_gemm_args;
+
+int sx_gemm(const sx_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-wise kernels (HBM-bound).  "act dtype" arguments are SX_F32 | SX_BF16; round_tf32 rounds fp32
+ * outputs that feed a TF32 GEMM.  Dropout masks are counter-based: keep(i) = hash(seed, flat index)
+ * >= p, so backward regenerates the forward mask from (seed, index) instead of storing it.
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[0] = max(x[0..n))                        -- voxels_pos.max(), segtran_shared.py:1231 */
+int sx_reduce_max(const float* x, int64_t n, float* out, void* stream);
+
+/* Learnable-sinusoid positional code, LearnedSinuPosEmbedder.forward (segtran_shared.py:989-998) with the
+ * pos/pos.max() normalisation of SegtranPosEncoder.forward (:1231).  pos [R,pd], W [C,pd], b [C] -> pe [R,C]. */
+int sx_pos_lsinu_fwd(const float* pos, const float* posmax, int64_t R, int32_t pd, const float* W, const float* b,
+                     int32_t C, float* pe, void* stream);
+/* dpe [R,C] -> dW [C,pd], db [C] accumulated (+=); de_scratch [R,C] is caller-provided scratch. */
+int sx_pos_lsinu_bwd(const float* pos, const float* posmax, int64_t R, int32_t pd, const float* W, const float* b,
+                     int32_t C, const float* dpe, float* de_scratch, float* dW, float* db, void* stream);
+
+/* Fused prologue of SegtranFusionEncoder.forward (segtran_shared.py:916, :930-934, :944-946):
+ *   h = mask * dropout( LN( LN_{g,b}(x) + posw * pe[..., :C] ) ),  x [B,N,C] fp32, pe rows of length C0,
+ *   pe_bstride = 0 when the code is shared by the batch; mask [B*N] fp32 or NULL; stats [B*N,4]. */
+int sx_prologue_fwd(const float* x, int64_t B, int32_t N, int32_t C, const float* g, const float* b, const float* pe,
+                    int32_t C0, int64_t pe_bstride, float posw, const float* mask, float drop_p, uint64_t seed, void* h,
+                    int32_t h_dtype, int32_t round_tf32, float* stats, void* stream);
+/* dh fp32 -> dx [B,N,C]; dg, db [C] and dpe (same addressing as pe, may be NULL) are accumulated (+=). */
+int sx_prologue_bwd(const float* dh, const float* x, int64_t B, int32_t N, int32_t C, const float* g, const float* b,
+                    const float* pe, int32_t C0, int64_t pe_bstride, float posw, const float* mask, float drop_p,
+                    uint64_t seed, const float* stats, float* dx, float* dg, float* db, float* dpe, void* stream);
+
+/* Row softmax with the reference's conditional clamp and attention dropout (segtran_shared.py:578-580, :601-605):
+ *   if (*amax > clip) S = clamp(S, -clip, clip);  P = dropout(softmax(S)).  S [R,L] fp32 (row stride lds),
+ *   P [R,L] (row stride ldp), lse [R] = log-sum-exp of the (clamped) row, kept for backward. */
+int sx_softmax_fwd(const float* S, int64_t R, int32_t L, int64_t lds, const float* amax, float clip, float drop_p,
+                   uint64_t seed, void* P, int32_t p_dtype, int64_t ldp, int32_t round_tf32, float* lse, void* stream);
+int sx_softmax_bwd(const float* dP, int64_t ldd, const float* S, int64_t lds, const float* lse, int64_t R, int32_t L,
+                   const float* amax, float clip, float drop_p, uint64_t seed, int64_t ldp_fwd, void* dS,
+                   int32_t ds_dtype, int64_t ldo, int32_t round_tf32, void* stream);
+
+/* LayerNorm with affine over rows, eps 1e-12 (first_norm_layer, segtran_shared.py:456).  stats [R,2]. */
+int sx_layernorm_fwd(const float* x, int64_t R, int32_t C, const float* g, const float* b, void* y, int32_t y_dtype,
+                     int32_t round_tf32, float* stats, void* stream);
+int sx_layernorm_bwd(const float* dy, const float* x, int64_t R, int32_t C, const float* g, const float* stats,
+                     void* dx, int32_t dx_dtype, int32_t round_tf32, float* dg, float* db, void* stream);
+
+/* MMPrivateOutput tail + LearnedSoftAggregate (segtran_shared.py:273-274, :318-325):
+ *   Yn = LN_{g,b}(dropout(Y));  w = softmax_modes(Yn.ws + bs);  out = sum_m w_m Yn_m
+ *   Y [B,M,N,F] fp32 -> out [B,N,F] fp32; stats [B,M,N,2]; wts [B,M,N]. */
+int sx_ln_softaggr_fwd(const float* Y, int32_t B, int32_t M, int32_t N, int32_t F, const float* g, const float* b,
+                       const float* ws, const float* bs, float drop_p, uint64_t seed, float* out, float* stats,
+                       float* wts, void* stream);
+int sx_ln_softaggr_bwd(const float* dout, const float* Y, int32_t B, int32_t M, int32_t N, int32_t F, const float* g,
+                       const float* b, const float* ws, float drop_p, uint64_t seed, const float* stats,
+                       const float* wts, void* dY, int32_t dy_dtype, int32_t round_tf32, float* dg, float* db,
+                       float* dws, float* dbs, void* stream);
+
+/* dH = dropout'(dG) * gelu'(H)  (MMSharedMid backward, segtran_shared.py:243-245) */
+int sx_gelu_bwd(const float* dG, const void* H, int32_t h_dtype, int64_t n, float drop_p, uint64_t seed, void* dH,
+                int32_t dh_dtype, int32_t round_tf32, void* stream);
+/* dtype conversion / TF32 rounding of a flat buffer (weights once per step) */
+int sx_convert(const void* x, int32_t x_dtype, int64_t n, void* y, int32_t y_dtype, int32_t round_tf32, void* stream);
+/* out[c] += sum_r X[r,c]   (bias gradients) */
+int sx_colsum(const void* X, int32_t x_dtype, int64_t R, int32_t C, int64_t ld, float* out, void* stream);
+/* batched transpose [Z,R,C] -> [Z,C,R] fp32: token flatten / scatter (segtran3d.py:328-330, :478-480) */
+int sx_transpose(const float* in, int64_t Z, int32_t R, int32_t C, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Segmentation head, collapsed form (segtran3d.py:364-367, :381-386, :488-496; segtran2d.py:304-306,
+ * :427, :435-436).  curr [B,Cf,V] fp32 channels-first, W [K,Cf], L / dL [B,K,V].
+ * ------------------------------------------------------------------------------------------- */
+int sx_head_contract_fwd(const float* curr, const float* W, const float* bias, int32_t B, int32_t Cf, int64_t V,
+                         int32_t K, float* L, int32_t accumulate, void* stream);
+int sx_head_contract_bwd_data(const float* dL, const float* W, int32_t B, int32_t Cf, int64_t V, int32_t K,
+                              float* dcurr, void* stream);
+int sx_head_contract_bwd_weight(const float* dL, const float* curr, int32_t B, int32_t Cf, int64_t V, int32_t K,
+                                float* dW, void* stream);
+/* 1-D linear resampling (align_corners=False) of x viewed as [outer, Lin, inner] -> [outer, Lout, inner];
+ * F.interpolate(mode='bilinear'|'trilinear') == one pass per axis. */
+int sx_resize_axis_fwd(const float* x, int64_t outer, int32_t Lin, int32_t Lout, int64_t inner, float* y,
+                       int32_t accumulate, void* stream);
+int sx_resize_axis_bwd(const float* dy, int64_t outer, int32_t Lin, int32_t Lout, int64_t inner, float* dx,
+                       void* stream);
+/* tiny strided fp32 GEMM on CUDA cores (class-dimension products of the collapsed head):
+ *   C[z](m,n) (+)= alpha * sum_k A[z](m,k) B[z](k,n), element strides given explicitly */
+int sx_sgemm_small(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int64_t sam, int64_t sak,
+                   int64_t sbk, int64_t sbn, int64_t scm, int64_t scn, int32_t Z, int64_t saz, int64_t sbz, int64_t scz,
+                   float alpha, int32_t accumulate, void* stream);
+
+/* debug knobs for bring-up (descriptor field overrides); not part of the stable ABI */
+int sx_gemm_debug_set(const char* key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGTRAN_B200_H_ */

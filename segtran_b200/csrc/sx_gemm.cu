@@ -1,0 +1,513 @@
+// Batched GEMM on the sm_100a 5th-gen tensor cores.
+//
+//   C[z][m][n] = epilogue(alpha * sum_k A[z][m][k] * B[z][n][k])
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor 4-D boxes, 128-byte swizzle, 4-stage mbarrier ring)
+//   warp 1      : MMA issuer    (one elected lane issues tcgen05.mma 128x256xK16/K8, accumulators in TMEM)
+//   warp 2      : TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
+//   warps 4..7  : epilogue      (tcgen05.ld -> registers -> bias/GELU/dropout/rounding -> global)
+// The epilogue of tile i overlaps the main loop of tile i+1 through the second TMEM accumulator.
+// Operands may be K-major or MN-major (both through canonical SWIZZLE_128B shared-memory layouts), so
+// forward (x W^T), data-gradient (dy W) and weight-gradient (dy^T x) products all run without transposes.
+// Operand arithmetic: kind::tf32 on fp32 storage (parity-grade) or kind::f16 on bf16 storage (fast).
+//
+// Replaces in the reference: nn.Linear / torch.matmul / grouped Conv1d call sites on the hot path,
+// code/networks/segtran_shared.py:243, :267, :414, :447, :559-560, :566 (and their autograd backward).
+#include <mutex>
+#include <string>
+
+#include "sx_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;          // tile rows   (UMMA M)
+constexpr int BN = 256;          // tile cols   (UMMA N)
+constexpr int BKB = 128;         // bytes of K per stage row (one 128B swizzle span)
+constexpr int KSTEPS = 4;        // UMMA instructions per stage (each covers 32 bytes of K)
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BKB;       // 16 KB
+constexpr int B_STAGE_BYTES = BN * BKB;       // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int TMEM_COLS = 512;
+constexpr int NUM_THREADS = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmParams {
+  int M, N, K, Z0, Z1;
+  int tiles_m, tiles_n, split_k, kb_per_split, num_kb, total_tiles;
+  int a_uses_z0, a_uses_z1, b_uses_z0, b_uses_z1;
+  void* C;
+  int c_bf16;
+  int round_tf32;
+  int c_vec_ok;
+  long long ldc, c_sz0, c_sz1;
+  float alpha;
+  int bias_mode;
+  const float* bias;
+  long long bias_sz0, bias_sz1;
+  int act;
+  int accumulate;
+  void* preact;
+  float* amax;
+  float drop_p;
+  unsigned long long drop_seed;
+  // descriptor fields (bring-up knobs; defaults are the canonical encodings)
+  unsigned int lbo_k, sbo_k, lbo_mn_a, lbo_mn_b, sbo_mn, desc_version;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t version, uint32_t layout_type) {
+  // cute::UMMA::SmemDescriptor: start[0,14) lbo[16,30) sbo[32,46) version[46,48) layout_type[61,64)
+  //   layout_type 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks; the only layout the
+  //   tensor core accepts for MN-major 32-bit (tf32) operands, cutlass sm100_common.inl:92)
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)(version & 0x3) << 46;
+  d |= (uint64_t)(layout_type & 0x7) << 61;
+  return d;
+}
+
+template <int ES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr bool kTF32 = (ES == 4);
+  constexpr int BK = BKB / ES;                 // elements of K per stage: 64 (bf16) / 32 (tf32)
+  constexpr int UMMA_K = 32 / ES;              // 16 / 8
+  constexpr int MN_BOX = BKB / ES;             // contiguous MN elements per MN-major box: 64 / 32
+  constexpr int MN_BOX_BYTES = BK * BKB;       // bytes of one MN-major box (BK rows of 128 B)
+  // descriptor start-address advance per UMMA k-step, in 16-byte units
+  constexpr uint32_t ADV_K = 32 >> 4;                        // K-major: 32 bytes along the swizzled row
+  constexpr uint32_t ADV_MN = (UMMA_K * BKB) >> 4;           // MN-major: UMMA_K rows of 128 B
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                   // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;         // [STAGES]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]       MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]     epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    sx::tma_prefetch_desc(&tmA);
+    sx::tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      sx::mbar_init(&full_bar[s], 1);
+      sx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      sx::mbar_init(&tfull_bar[a], 1);
+      sx::mbar_init(&tempty_bar[a], 4);
+    }
+    sx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    sx::tmem_alloc(tmem_slot, TMEM_COLS);
+    sx::tmem_relinquish();
+  }
+  sx::tc_fence_before();
+  __syncthreads();
+  sx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int t, int& z0, int& z1, int& mb, int& nb, int& ks) {
+    nb = t % p.tiles_n; t /= p.tiles_n;
+    mb = t % p.tiles_m; t /= p.tiles_m;
+    ks = t % p.split_k; t /= p.split_k;
+    z0 = t % p.Z0;
+    z1 = t / p.Z0;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (sx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int z0, z1, mb, nb, ks;
+        decode(t, z0, z1, mb, nb, ks);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int az0 = p.a_uses_z0 ? z0 : 0, az1 = p.a_uses_z1 ? z1 : 0;
+        const int bz0 = p.b_uses_z0 ? z0 : 0, bz1 = p.b_uses_z1 ? z1 : 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          sx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          sx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          const int k0 = kb * BK;
+          if constexpr (!A_MN) {
+            sx::tma_load_4d(sa, &tmA, &full_bar[stage], k0, mb * BM, az0, az1);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / MN_BOX; ++j)
+              sx::tma_load_4d(sa + j * MN_BOX_BYTES, &tmA, &full_bar[stage], mb * BM + j * MN_BOX, k0, az0, az1);
+          }
+          if constexpr (!B_MN) {
+            sx::tma_load_4d(sb, &tmB, &full_bar[stage], k0, nb * BN, bz0, bz1);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / MN_BOX; ++j)
+              sx::tma_load_4d(sb + j * MN_BOX_BYTES, &tmB, &full_bar[stage], nb * BN + j * MN_BOX, k0, bz0, bz1);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // cute::UMMA::InstrDescriptor: c_format[4,6)=1 (F32), a_format[7,10), b_format[10,13) (1=BF16, 2=TF32),
+    // a_major bit 15, b_major bit 16 (1 = MN-major), n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
+    constexpr uint32_t fmt = kTF32 ? 2u : 1u;
+    constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) |
+                               ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      int z0, z1, mb, nb, ks;
+      decode(t, z0, z1, mb, nb, ks);
+      const int kb0 = ks * p.kb_per_split;
+      const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      sx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      sx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        sx::mbar_wait(&full_bar[stage], phase);
+        sx::tc_fence_after();
+        if (sx::elect_one()) {
+          const uint32_t sa = sx::smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          constexpr uint32_t LT_MN = kTF32 ? 1u : 2u;
+          const uint64_t da = A_MN ? make_smem_desc(sa, p.lbo_mn_a, p.sbo_mn, p.desc_version, LT_MN)
+                                   : make_smem_desc(sa, p.lbo_k, p.sbo_k, p.desc_version, 2u);
+          const uint64_t db = B_MN ? make_smem_desc(sb, p.lbo_mn_b, p.sbo_mn, p.desc_version, LT_MN)
+                                   : make_smem_desc(sb, p.lbo_k, p.sbo_k, p.desc_version, 2u);
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k) {
+            const uint64_t dak = da + (uint64_t)(k * (A_MN ? ADV_MN : ADV_K));
+            const uint64_t dbk = db + (uint64_t)(k * (B_MN ? ADV_MN : ADV_K));
+            sx::umma<kTF32>(tmem_d, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          sx::umma_commit(&empty_bar[stage]);                 // frees the smem stage when these MMAs retire
+          if (kb == kb1 - 1) sx::umma_commit(&tfull_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    int it = 0;
+    float tmax = -3.0e38f;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      int z0, z1, mb, nb, ks;
+      decode(t, z0, z1, mb, nb, ks);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      sx::mbar_wait(&tfull_bar[acc], acc_phase);
+      sx::tc_fence_after();
+      const int row = mb * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const long long zoff = (long long)z1 * p.c_sz1 + (long long)z0 * p.c_sz0;
+      const long long roff = zoff + (long long)row * p.ldc;
+      const float* bias = p.bias ? p.bias + (long long)z1 * p.bias_sz1 + (long long)z0 * p.bias_sz0 : nullptr;
+      const bool add_bias = (bias != nullptr) && (ks == 0);
+      const float bias_m = (add_bias && p.bias_mode == SX_BIAS_M && row_ok) ? bias[row] : 0.f;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = nb * BN + c * 32;
+        if (col0 >= p.N) break;                 // warp-uniform
+        uint32_t v[32];
+        sx::tmem_ld32(taddr + c * 32, v);
+        sx::tmem_ld_wait();
+        if (row_ok) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) * p.alpha + bias_m;
+            if (add_bias && p.bias_mode == SX_BIAS_N && col0 + j < p.N) x += bias[col0 + j];
+            f[j] = x;
+          }
+          const bool full = (col0 + 32 <= p.N) && p.c_vec_ok;
+          if (p.preact) {
+            if (p.c_bf16) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.preact) + roff + col0;
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = __float2bfloat16_rn(f[j]);
+            } else {
+              float* o = reinterpret_cast<float*>(p.preact) + roff + col0;
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) o[j] = f[j];
+              }
+            }
+          }
+          if (p.act == SX_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = sx::gelu_erf(f[j]);
+          }
+          if (p.drop_p > 0.f) {
+            const float keep_scale = 1.f / (1.f - p.drop_p);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float u = sx::uniform_hash(p.drop_seed, (unsigned long long)(roff + col0 + j));
+              f[j] = (u >= p.drop_p) ? f[j] * keep_scale : 0.f;
+            }
+          }
+          if (p.round_tf32 && !p.c_bf16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = sx::round_tf32(f[j]);
+          }
+          if (p.amax) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) tmax = fmaxf(tmax, f[j]);
+          }
+          if (p.c_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.C) + roff + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(o + j) = pk;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = __float2bfloat16_rn(f[j]);
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.C) + roff + col0;
+            if (p.accumulate) {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(o + j, f[j]);
+            } else if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = f[j];
+            }
+          }
+        }
+      }
+      sx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sx::mbar_arrive(&tempty_bar[acc]);
+    }
+    if (p.amax) {
+      tmax = sx::warp_max(tmax);
+      if (lane == 0 && tmax > -3.0e38f) sx::atomic_max_float(p.amax, tmax);
+    }
+  }
+
+  sx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    sx::tc_fence_after();
+    sx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  });
+  return fn;
+}
+
+struct DebugKnobs {
+  long long lbo_k = 16, sbo_k = 1024, sbo_mn = -1, desc_version = 1;   // sbo_mn -1: canonical (1024 B; 512 B for tf32)
+  long long lbo_mn_a = -1, lbo_mn_b = -1;     // -1: canonical (BK rows * 128 B)
+  long long max_ctas = -1;
+};
+DebugKnobs g_knobs;
+
+int make_map(CUtensorMap* tm, const sx_operand& op, int es, int rows, int K, int Z0, int Z1, int box_rows,
+             const char* name) {
+  PFN_encodeTiled enc = get_encode();
+  SX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  SX_REQUIRE((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0, "sx_gemm: operand %s not 16-byte aligned", name);
+  SX_REQUIRE((op.ld * es) % 16 == 0, "sx_gemm: operand %s ld*elsize (%lld) not a multiple of 16", name,
+             (long long)op.ld * es);
+  const int z0 = op.stride_z0 ? Z0 : 1, z1 = op.stride_z1 ? Z1 : 1;
+  SX_REQUIRE((op.stride_z0 * es) % 16 == 0 && (op.stride_z1 * es) % 16 == 0,
+             "sx_gemm: operand %s batch strides not multiples of 16 bytes", name);
+  const int inner = BKB / es;      // elements in a 128-byte span
+  cuuint64_t gdim[4];
+  cuuint64_t gstr[3];
+  cuuint32_t box[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (op.major == SX_MAJOR_K) {
+    gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)rows;
+    box[0] = inner; box[1] = box_rows;
+  } else {
+    gdim[0] = (cuuint64_t)rows; gdim[1] = (cuuint64_t)K;
+    box[0] = inner; box[1] = inner;            // BK rows of k, each 128 B of mn
+  }
+  gdim[2] = z0; gdim[3] = z1;
+  box[2] = 1; box[3] = 1;
+  gstr[0] = (cuuint64_t)op.ld * es;
+  const cuuint64_t dflt = gstr[0] * gdim[1];
+  gstr[1] = op.stride_z0 ? (cuuint64_t)op.stride_z0 * es : dflt;
+  gstr[2] = op.stride_z1 ? (cuuint64_t)op.stride_z1 * es : (gstr[1] * gdim[2]);
+  CUtensorMapDataType dt = (es == 4) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  // MN-major fp32 (tf32) operands use the 32-byte-atom flavour of the 128-byte swizzle (UMMA SWIZZLE_128B_BASE32B)
+  const CUtensorMapSwizzle sw = (es == 4 && op.major == SX_MAJOR_MN) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                                                     : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(tm, dt, 4, const_cast<void*>(op.ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SX_REQUIRE(r == CUDA_SUCCESS,
+             "cuTensorMapEncodeTiled(%s) failed: %d (gdim %llu,%llu,%llu,%llu gstr %llu,%llu,%llu box %u,%u)", name,
+             (int)r, (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
+             (unsigned long long)gdim[3], (unsigned long long)gstr[0], (unsigned long long)gstr[1],
+             (unsigned long long)gstr[2], box[0], box[1]);
+  return 0;
+}
+
+template <int ES, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
+  auto kern = sx_gemm_kernel<ES, A_MN, B_MN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  SX_CHECK_CUDA(attr_err);
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sm_count_cached() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+  }
+  return n;
+}
+
+}  // namespace
+
+extern "C" int sx_gemm_debug_set(const char* key, int64_t value) {
+  std::string k(key);
+  if (k == "lbo_k") g_knobs.lbo_k = value;
+  else if (k == "sbo_k") g_knobs.sbo_k = value;
+  else if (k == "sbo_mn") g_knobs.sbo_mn = value;
+  else if (k == "lbo_mn_a") g_knobs.lbo_mn_a = value;
+  else if (k == "lbo_mn_b") g_knobs.lbo_mn_b = value;
+  else if (k == "desc_version") g_knobs.desc_version = value;
+  else if (k == "max_ctas") g_knobs.max_ctas = value;
+  else {
+    sx_set_error("sx_gemm_debug_set: unknown key %s", key);
+    return -1;
+  }
+  return 0;
+}
+
+extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
+  SX_REQUIRE(a != nullptr, "sx_gemm: null args");
+  SX_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->Z0 > 0 && a->Z1 > 0, "sx_gemm: bad shape M=%d N=%d K=%d Z=%dx%d",
+             a->M, a->N, a->K, a->Z0, a->Z1);
+  SX_REQUIRE(a->op_dtype == SX_OP_TF32 || a->op_dtype == SX_OP_BF16, "sx_gemm: bad op_dtype %d", a->op_dtype);
+  SX_REQUIRE(a->C != nullptr && a->A.ptr != nullptr && a->B.ptr != nullptr, "sx_gemm: null pointer");
+  const int es = a->op_dtype == SX_OP_TF32 ? 4 : 2;
+  const int bk = BKB / es;
+  const int sms = sm_count_cached();
+  SX_REQUIRE(sms > 0, "sx_gemm: no CUDA device (this library has no CPU fallback)");
+
+  GemmParams p{};
+  p.M = a->M; p.N = a->N; p.K = a->K; p.Z0 = a->Z0; p.Z1 = a->Z1;
+  p.tiles_m = sx_ceil_div(a->M, BM);
+  p.tiles_n = sx_ceil_div(a->N, BN);
+  p.num_kb = sx_ceil_div(a->K, bk);
+  int split = a->split_k < 1 ? 1 : a->split_k;
+  if (split > p.num_kb) split = p.num_kb;
+  p.kb_per_split = sx_ceil_div(p.num_kb, split);
+  p.split_k = sx_ceil_div(p.num_kb, p.kb_per_split);      // no empty splits
+  SX_REQUIRE(p.split_k == 1 || (a->accumulate && a->c_dtype == SX_F32 && a->act == SX_ACT_NONE && !a->preact &&
+                                a->drop_p == 0.f && !a->amax),
+             "sx_gemm: split_k > 1 needs accumulate=1 into fp32 C and a linear epilogue");
+  SX_REQUIRE(!a->accumulate || a->c_dtype == SX_F32, "sx_gemm: accumulate needs fp32 C");
+  const long long tt = (long long)p.tiles_m * p.tiles_n * p.split_k * a->Z0 * a->Z1;
+  SX_REQUIRE(tt < (1ll << 30), "sx_gemm: too many tiles");
+  p.total_tiles = (int)tt;
+  p.a_uses_z0 = a->A.stride_z0 != 0; p.a_uses_z1 = a->A.stride_z1 != 0;
+  p.b_uses_z0 = a->B.stride_z0 != 0; p.b_uses_z1 = a->B.stride_z1 != 0;
+  p.C = a->C; p.c_bf16 = a->c_dtype == SX_BF16; p.round_tf32 = a->round_tf32;
+  p.ldc = a->ldc; p.c_sz0 = a->c_stride_z0; p.c_sz1 = a->c_stride_z1;
+  const int vec = p.c_bf16 ? 8 : 4;
+  p.c_vec_ok = ((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && (a->ldc % vec == 0) && (a->c_stride_z0 % vec == 0) &&
+               (a->c_stride_z1 % vec == 0) &&
+               (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0);
+  p.alpha = a->alpha; p.bias_mode = a->bias ? a->bias_mode : SX_BIAS_NONE; p.bias = a->bias;
+  p.bias_sz0 = a->bias_stride_z0; p.bias_sz1 = a->bias_stride_z1;
+  p.act = a->act; p.accumulate = a->accumulate; p.preact = a->preact; p.amax = a->amax;
+  p.drop_p = a->drop_p; p.drop_seed = a->drop_seed;
+  p.lbo_k = (unsigned)g_knobs.lbo_k; p.sbo_k = (unsigned)g_knobs.sbo_k; p.sbo_mn = (unsigned)(g_knobs.sbo_mn >= 0 ? g_knobs.sbo_mn : (es == 4 ? 512 : 1024));
+  p.lbo_mn_a = (unsigned)(g_knobs.lbo_mn_a >= 0 ? g_knobs.lbo_mn_a : bk * BKB);
+  p.lbo_mn_b = (unsigned)(g_knobs.lbo_mn_b >= 0 ? g_knobs.lbo_mn_b : bk * BKB);
+  p.desc_version = (unsigned)g_knobs.desc_version;
+
+  CUtensorMap ta, tb;
+  int rc = make_map(&ta, a->A, es, a->M, a->K, a->Z0, a->Z1, BM, "A");
+  if (rc) return rc;
+  rc = make_map(&tb, a->B, es, a->N, a->K, a->Z0, a->Z1, BN, "B");
+  if (rc) return rc;
+
+  int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (g_knobs.max_ctas > 0 && grid > g_knobs.max_ctas) grid = (int)g_knobs.max_ctas;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool amn = a->A.major == SX_MAJOR_MN, bmn = a->B.major == SX_MAJOR_MN;
+  if (es == 4) {
+    if (!amn && !bmn) return launch<4, false, false>(ta, tb, p, grid, st);
+    if (!amn && bmn) return launch<4, false, true>(ta, tb, p, grid, st);
+    if (amn && !bmn) return launch<4, true, false>(ta, tb, p, grid, st);
+    return launch<4, true, true>(ta, tb, p, grid, st);
+  } else {
+    if (!amn && !bmn) return launch<2, false, false>(ta, tb, p, grid, st);
+    if (!amn && bmn) return launch<2, false, true>(ta, tb, p, grid, st);
+    if (amn && !bmn) return launch<2, true, false>(ta, tb, p, grid, st);
+    return launch<2, true, true>(ta, tb, p, grid, st);
+  }
+}

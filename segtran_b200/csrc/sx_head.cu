@@ -1,0 +1,294 @@
+// Voxel-wise segmentation head in collapsed form and its building blocks.
+//
+// Reference (segtran3d.py:364-367, 381-386, 488-496; segtran2d.py:304-306, 427, 435-436):
+//   logits = interp_out( conv_cls( interp_D( conv_bridge(curr) + interp(vfeat_fused) ) ) )
+// Every stage is linear and interpolation weights sum to one, so
+//   logits = interp_out( interp_D( (Wc Wb) curr + interp(Wc vfeat) + Wc bb + bc ) )
+// which turns a Cf->F conv over every voxel plus three F-channel full-resolution tensors into ONE pass over
+// `curr` producing `num_classes` channels (HBM-bound: curr is read exactly once, forward and backward).
+//
+//   head_contract_fwd        L[b,k,v]   = sum_c W[k,c] curr[b,c,v] + bias[k]          (reads curr)
+//   head_contract_bwd_data   dcurr[b,c,v] = sum_k W[k,c] dL[b,k,v]                    (writes dcurr)
+//   head_contract_bwd_weight dW[k,c]   += sum_{b,v} dL[b,k,v] curr[b,c,v]             (reads curr)
+//   resize_axis_fwd / _bwd   1-D linear resampling along one axis (align_corners=False), PyTorch semantics;
+//                            tri/bi-linear interpolation is applied as a sequence of axis passes.
+//   sgemm_small              strided fp32 GEMM on CUDA cores for the tiny class-dimension products.
+#include "sx_common.cuh"
+
+namespace {
+
+constexpr int MAXK = 8;          // max classes handled per pass
+
+// ---- forward contraction: block = 128 threads x float4 = 512 voxels, loop over channels ----
+template <int VEC>
+__global__ void __launch_bounds__(128)
+head_contract_fwd_kernel(const float* __restrict__ curr, const float* __restrict__ W, const float* __restrict__ bias,
+                         int Cf, long long V, int K, float* __restrict__ L, int accumulate) {
+  extern __shared__ float sW[];             // [K][Cf]
+  for (int i = threadIdx.x; i < K * Cf; i += blockDim.x) sW[i] = W[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const long long v0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (v0 >= V) return;
+  const float* src = curr + (long long)b * Cf * V + v0;
+  float acc[MAXK][VEC];
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < Cf; ++c) {
+    float x[VEC];
+    if constexpr (VEC == 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src + (long long)c * V));
+      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else {
+      x[0] = __ldg(src + (long long)c * V);
+    }
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k)
+      if (k < K) {
+        const float w = sW[k * Cf + c];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[k][j] = fmaf(w, x[j], acc[k][j]);
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k)
+    if (k < K) {
+      float* dst = L + ((long long)b * K + k) * V + v0;
+      const float bk = bias ? bias[k] : 0.f;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float r = acc[k][j] + bk;
+        dst[j] = accumulate ? dst[j] + r : r;
+      }
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(128)
+head_contract_bwd_data_kernel(const float* __restrict__ dL, const float* __restrict__ W, int Cf, long long V, int K,
+                              float* __restrict__ dcurr) {
+  extern __shared__ float sW[];
+  for (int i = threadIdx.x; i < K * Cf; i += blockDim.x) sW[i] = W[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const long long v0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (v0 >= V) return;
+  float g[MAXK][VEC];
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) g[k][j] = (k < K) ? dL[((long long)b * K + k) * V + v0 + j] : 0.f;
+  float* dst = dcurr + (long long)b * Cf * V + v0;
+#pragma unroll 4
+  for (int c = 0; c < Cf; ++c) {
+    float o[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k)
+      if (k < K) {
+        const float w = sW[k * Cf + c];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] = fmaf(w, g[k][j], o[j]);
+      }
+    if constexpr (VEC == 4)
+      *reinterpret_cast<float4*>(dst + (long long)c * V) = make_float4(o[0], o[1], o[2], o[3]);
+    else
+      dst[(long long)c * V] = o[0];
+  }
+}
+
+// one warp per channel; lanes stride over a voxel chunk; dW[k,c] += sum_v dL[k,v] curr[c,v]
+__global__ void __launch_bounds__(256)
+head_contract_bwd_weight_kernel(const float* __restrict__ dL, const float* __restrict__ curr, int Cf, long long V,
+                                int K, long long chunk, float* __restrict__ dW) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + warp;
+  const int b = blockIdx.z;
+  const long long v_begin = (long long)blockIdx.y * chunk;
+  long long v_end = v_begin + chunk;
+  if (v_end > V) v_end = V;
+  if (c >= Cf) return;
+  const float* x = curr + ((long long)b * Cf + c) * V;
+  const float* g = dL + (long long)b * K * V;
+  float acc[MAXK];
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k) acc[k] = 0.f;
+  for (long long v = v_begin + lane; v < v_end; v += 32) {
+    const float xv = __ldg(x + v);
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k)
+      if (k < K) acc[k] = fmaf(xv, g[(long long)k * V + v], acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k)
+    if (k < K) {
+      const float s = sx::warp_sum(acc[k]);
+      if (lane == 0) atomicAdd(&dW[k * Cf + c], s);
+    }
+}
+
+// ---- 1-D linear resize along one axis of x viewed as [outer, Lin, inner] -> [outer, Lout, inner] ----
+__device__ __forceinline__ void src_index(int j, float scale, int Lin, int& i0, int& i1, float& w1) {
+  float s = ((float)j + 0.5f) * scale - 0.5f;       // area_pixel_compute_source_index, align_corners=False
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  if (i0 > Lin - 1) i0 = Lin - 1;
+  i1 = i0 + ((i0 < Lin - 1) ? 1 : 0);
+  w1 = s - (float)i0;
+}
+
+__global__ void resize_axis_fwd_kernel(const float* __restrict__ x, long long outer, int Lin, int Lout, long long inner,
+                                       float* __restrict__ y, int accumulate) {
+  const float scale = (float)Lin / (float)Lout;
+  const long long total = outer * Lout * inner;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long in = idx % inner;
+    const long long t = idx / inner;
+    const int j = (int)(t % Lout);
+    const long long o = t / Lout;
+    int i0, i1;
+    float w1;
+    src_index(j, scale, Lin, i0, i1, w1);
+    const float* base = x + o * Lin * inner + in;
+    const float v = (1.f - w1) * base[(long long)i0 * inner] + w1 * base[(long long)i1 * inner];
+    y[idx] = accumulate ? y[idx] + v : v;
+  }
+}
+
+// adjoint (gather form): dx[o,i,in] = sum_j w(j->i) dy[o,j,in]
+__global__ void resize_axis_bwd_kernel(const float* __restrict__ dy, long long outer, int Lin, int Lout,
+                                       long long inner, float* __restrict__ dx) {
+  const float scale = (float)Lin / (float)Lout;
+  const float inv = (float)Lout / (float)Lin;
+  const long long total = outer * Lin * inner;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long in = idx % inner;
+    const long long t = idx / inner;
+    const int i = (int)(t % Lin);
+    const long long o = t / Lin;
+    int jlo = (int)floorf(((float)i - 1.f + 0.5f) * inv - 0.5f) - 1;
+    int jhi = (int)ceilf(((float)i + 1.f + 0.5f) * inv - 0.5f) + 1;
+    if (i == 0) jlo = 0;                       // clamped sources (s < 0) map to i = 0
+    if (i == Lin - 1) jhi = Lout - 1;
+    if (jlo < 0) jlo = 0;
+    if (jhi > Lout - 1) jhi = Lout - 1;
+    const float* base = dy + o * Lout * inner + in;
+    float acc = 0.f;
+    for (int j = jlo; j <= jhi; ++j) {
+      int i0, i1;
+      float w1;
+      src_index(j, scale, Lin, i0, i1, w1);
+      float w = 0.f;
+      if (i0 == i) w += 1.f - w1;
+      if (i1 == i) w += w1;
+      if (w != 0.f) acc = fmaf(w, base[(long long)j * inner], acc);
+    }
+    dx[idx] = acc;
+  }
+}
+
+// ---- tiny strided fp32 GEMM: C[z][m][n] (+)= alpha * sum_k A[z](m,k) B[z](k,n) ----
+__global__ void sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                   int M, int N, int K, long long sam, long long sak, long long sbk, long long sbn,
+                                   long long scm, long long scn, long long saz, long long sbz, long long scz, float alpha,
+                                   int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y * blockDim.y + threadIdx.y;
+  const long long z = blockIdx.z;
+  if (m >= M || n >= N) return;
+  const float* a = A + z * saz + (long long)m * sam;
+  const float* b = B + z * sbz + (long long)n * sbn;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(a[(long long)k * sak], b[(long long)k * sbk], acc);
+  float* c = C + z * scz + (long long)m * scm + (long long)n * scn;
+  *c = accumulate ? *c + alpha * acc : alpha * acc;
+}
+
+}  // namespace
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int sx_head_contract_fwd(const float* curr, const float* W, const float* bias, int32_t B, int32_t Cf,
+                                    int64_t V, int32_t K, float* L, int32_t accumulate, void* stream) {
+  SX_REQUIRE(K >= 1 && K <= MAXK, "sx_head_contract_fwd: num_classes %d not in 1..%d", K, MAXK);
+  const size_t smem = (size_t)K * Cf * 4;
+  SX_REQUIRE(smem <= 48 * 1024, "sx_head_contract_fwd: K*Cf=%d too large", K * Cf);
+  const bool vec4 = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(curr) & 15) == 0);
+  if (vec4) {
+    dim3 grid(sx_ceil_div(V, 128 * 4), B);
+    head_contract_fwd_kernel<4><<<grid, 128, smem, ST(stream)>>>(curr, W, bias, Cf, V, K, L, accumulate);
+  } else {
+    dim3 grid(sx_ceil_div(V, 128), B);
+    head_contract_fwd_kernel<1><<<grid, 128, smem, ST(stream)>>>(curr, W, bias, Cf, V, K, L, accumulate);
+  }
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_head_contract_bwd_data(const float* dL, const float* W, int32_t B, int32_t Cf, int64_t V, int32_t K,
+                                         float* dcurr, void* stream) {
+  SX_REQUIRE(K >= 1 && K <= MAXK, "sx_head_contract_bwd_data: num_classes %d not in 1..%d", K, MAXK);
+  const size_t smem = (size_t)K * Cf * 4;
+  SX_REQUIRE(smem <= 48 * 1024, "sx_head_contract_bwd_data: K*Cf=%d too large", K * Cf);
+  const bool vec4 = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(dcurr) & 15) == 0);
+  if (vec4) {
+    dim3 grid(sx_ceil_div(V, 128 * 4), B);
+    head_contract_bwd_data_kernel<4><<<grid, 128, smem, ST(stream)>>>(dL, W, Cf, V, K, dcurr);
+  } else {
+    dim3 grid(sx_ceil_div(V, 128), B);
+    head_contract_bwd_data_kernel<1><<<grid, 128, smem, ST(stream)>>>(dL, W, Cf, V, K, dcurr);
+  }
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_head_contract_bwd_weight(const float* dL, const float* curr, int32_t B, int32_t Cf, int64_t V,
+                                           int32_t K, float* dW, void* stream) {
+  SX_REQUIRE(K >= 1 && K <= MAXK, "sx_head_contract_bwd_weight: num_classes %d not in 1..%d", K, MAXK);
+  long long chunk = 8192;
+  int chunks = sx_ceil_div(V, chunk);
+  if (chunks > 65535) { chunk = (V + 65534) / 65535; chunks = sx_ceil_div(V, chunk); }
+  dim3 grid(sx_ceil_div(Cf, 8), chunks, B);
+  head_contract_bwd_weight_kernel<<<grid, 256, 0, ST(stream)>>>(dL, curr, Cf, V, K, chunk, dW);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int ew_grid(long long total) {
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" int sx_resize_axis_fwd(const float* x, int64_t outer, int32_t Lin, int32_t Lout, int64_t inner, float* y,
+                                  int32_t accumulate, void* stream) {
+  resize_axis_fwd_kernel<<<ew_grid(outer * Lout * inner), 256, 0, ST(stream)>>>(x, outer, Lin, Lout, inner, y,
+                                                                               accumulate);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_resize_axis_bwd(const float* dy, int64_t outer, int32_t Lin, int32_t Lout, int64_t inner, float* dx,
+                                  void* stream) {
+  resize_axis_bwd_kernel<<<ew_grid(outer * Lin * inner), 256, 0, ST(stream)>>>(dy, outer, Lin, Lout, inner, dx);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_sgemm_small(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int64_t sam,
+                              int64_t sak, int64_t sbk, int64_t sbn, int64_t scm, int64_t scn, int32_t Z, int64_t saz,
+                              int64_t sbz, int64_t scz, float alpha, int32_t accumulate, void* stream) {
+  SX_REQUIRE(Z >= 1 && Z <= 65535, "sx_sgemm_small: batch %d out of range", Z);
+  dim3 blk(32, 8), grid(sx_ceil_div(N, 32), sx_ceil_div(M, 8), Z);
+  sgemm_small_kernel<<<grid, blk, 0, ST(stream)>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, scm, scn, saz, sbz, scz, alpha,
+                                                   accumulate);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
