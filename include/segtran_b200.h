@@ -118,9 +118,12 @@ int sx_prologue_bwd(const float* dh, const float* x, int64_t B, int32_t N, int32
 
 /* Row softmax with the reference's conditional clamp and attention dropout (segtran_shared.py:578-580, :601-605):
  *   if (*amax > clip) S = clamp(S, -clip, clip);  P = dropout(softmax(S)).  S [R,L] fp32 (row stride lds),
- *   P [R,L] (row stride ldp), lse [R] = log-sum-exp of the (clamped) row, kept for backward. */
+ *   P [R,L] (row stride ldp), lse [R] = log-sum-exp of the (clamped) row, kept for backward.
+ *   diag (optional, device float[2]): [0] = running max of *amax, [1] += 1 when the clamp fired — the module's
+ *   max_attn / clamp_count counters (:575-587) without the reference's two .item() host syncs per call. */
 int sx_softmax_fwd(const float* S, int64_t R, int32_t L, int64_t lds, const float* amax, float clip, float drop_p,
-                   uint64_t seed, void* P, int32_t p_dtype, int64_t ldp, int32_t round_tf32, float* lse, void* stream);
+                   uint64_t seed, void* P, int32_t p_dtype, int64_t ldp, int32_t round_tf32, float* lse, float* diag,
+                   void* stream);
 int sx_softmax_bwd(const float* dP, int64_t ldd, const float* S, int64_t lds, const float* lse, int64_t R, int32_t L,
                    const float* amax, float clip, float drop_p, uint64_t seed, int64_t ldp_fwd, void* dS,
                    int32_t ds_dtype, int64_t ldo, int32_t round_tf32, void* stream);

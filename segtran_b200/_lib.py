@@ -1,0 +1,100 @@
+"""ctypes binding of libsegtran_b200.so (the C ABI declared in include/segtran_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make``.  There is no fallback:
+if the shared object is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsegtran_b200.so")
+
+SX_F32, SX_BF16 = 0, 1
+SX_OP_TF32, SX_OP_BF16 = 0, 1
+SX_MAJOR_K, SX_MAJOR_MN = 0, 1
+SX_BIAS_NONE, SX_BIAS_N, SX_BIAS_M = 0, 1, 2
+SX_ACT_NONE, SX_ACT_GELU = 0, 1
+
+
+class SxError(RuntimeError):
+    pass
+
+
+class sx_operand(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("major", C.c_int32), ("_pad", C.c_int32), ("ld", C.c_int64),
+                ("stride_z0", C.c_int64), ("stride_z1", C.c_int64)]
+
+
+class sx_gemm_args(C.Structure):
+    _fields_ = [("op_dtype", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("Z0", C.c_int32),
+                ("Z1", C.c_int32), ("A", sx_operand), ("B", sx_operand), ("C", C.c_void_p), ("c_dtype", C.c_int32),
+                ("round_tf32", C.c_int32), ("ldc", C.c_int64), ("c_stride_z0", C.c_int64), ("c_stride_z1", C.c_int64),
+                ("alpha", C.c_float), ("bias_mode", C.c_int32), ("bias", C.c_void_p), ("bias_stride_z0", C.c_int64),
+                ("bias_stride_z1", C.c_int64), ("act", C.c_int32), ("accumulate", C.c_int32), ("preact", C.c_void_p),
+                ("split_k", C.c_int32), ("_pad2", C.c_int32), ("amax", C.c_void_p), ("drop_p", C.c_float),
+                ("_pad3", C.c_uint32), ("drop_seed", C.c_uint64)]
+
+
+_P, _I, _L, _F, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
+
+# name -> argtypes (every function returns int; 0 = success)
+_PROTOS = {
+    "sx_gemm": [C.POINTER(sx_gemm_args), _P],
+    "sx_gemm_debug_set": [C.c_char_p, _L],
+    "sx_reduce_max": [_P, _L, _P, _P],
+    "sx_pos_lsinu_fwd": [_P, _P, _L, _I, _P, _P, _I, _P, _P],
+    "sx_pos_lsinu_bwd": [_P, _P, _L, _I, _P, _P, _I, _P, _P, _P, _P, _P],
+    "sx_prologue_fwd": [_P, _L, _I, _I, _P, _P, _P, _I, _L, _F, _P, _F, _U64, _P, _I, _I, _P, _P],
+    "sx_prologue_bwd": [_P, _P, _L, _I, _I, _P, _P, _P, _I, _L, _F, _P, _F, _U64, _P, _P, _P, _P, _P, _P],
+    "sx_softmax_fwd": [_P, _L, _I, _L, _P, _F, _F, _U64, _P, _I, _L, _I, _P, _P, _P],
+    "sx_softmax_bwd": [_P, _L, _P, _L, _P, _L, _I, _P, _F, _F, _U64, _L, _P, _I, _L, _I, _P],
+    "sx_layernorm_fwd": [_P, _L, _I, _P, _P, _P, _I, _I, _P, _P],
+    "sx_layernorm_bwd": [_P, _P, _L, _I, _P, _P, _P, _I, _I, _P, _P, _P],
+    "sx_ln_softaggr_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _F, _U64, _P, _P, _P, _P],
+    "sx_ln_softaggr_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _U64, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
+    "sx_gelu_bwd": [_P, _P, _I, _L, _F, _U64, _P, _I, _I, _P],
+    "sx_convert": [_P, _I, _L, _P, _I, _I, _P],
+    "sx_colsum": [_P, _I, _L, _I, _L, _P, _P],
+    "sx_transpose": [_P, _L, _I, _I, _P, _P],
+    "sx_head_contract_fwd": [_P, _P, _P, _I, _I, _L, _I, _P, _I, _P],
+    "sx_head_contract_bwd_data": [_P, _P, _I, _I, _L, _I, _P, _P],
+    "sx_head_contract_bwd_weight": [_P, _P, _I, _I, _L, _I, _P, _P],
+    "sx_resize_axis_fwd": [_P, _L, _I, _I, _L, _P, _I, _P],
+    "sx_resize_axis_bwd": [_P, _L, _I, _I, _L, _P, _P],
+    "sx_sgemm_small": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _L, _L, _L, _F, _I, _P],
+}
+# every symbol include/segtran_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = sorted(list(_PROTOS) + ["sx_version", "sx_last_error", "sx_device_info"])
+
+_lib = None
+
+
+def lib():
+    """The loaded CDLL; raises if the extension has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise SxError("segtran_b200: %s is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make` at the repo root (there is no CPU / PyTorch fallback)" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        l.sx_version.restype = C.c_int
+        l.sx_last_error.restype = C.c_char_p
+        l.sx_device_info.argtypes = [C.POINTER(C.c_int)] * 3
+        l.sx_device_info.restype = C.c_int
+        for name, at in _PROTOS.items():
+            f = getattr(l, name)
+            f.argtypes = at
+            f.restype = C.c_int
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise SxError("%s failed (rc=%d): %s" % (what, rc, lib().sx_last_error().decode("utf-8", "replace")))
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)

@@ -234,12 +234,17 @@ __global__ void prologue_bwd_kernel(const float* __restrict__ dh, const float* _
 template <typename T>
 __global__ void softmax_fwd_kernel(const float* __restrict__ S, long long R, int L, long long lds,
                                    const float* __restrict__ amax, float clip, float drop_p, unsigned long long seed,
-                                   T* __restrict__ P, long long ldp, float* __restrict__ lse, int rnd) {
+                                   T* __restrict__ P, long long ldp, float* __restrict__ lse, int rnd,
+                                   float* __restrict__ diag) {
   extern __shared__ float sm[];
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* row = sm + (long long)warp * L;
   const bool do_clip = amax && (*amax > clip);
+  if (diag && amax && blockIdx.x == 0 && threadIdx.x == 0) {
+    diag[0] = fmaxf(diag[0], *amax);
+    if (do_clip) diag[1] += 1.f;
+  }
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   for (long long r = (long long)blockIdx.x * warps + warp; r < R; r += (long long)gridDim.x * warps) {
     const float* sr = S + r * lds;
@@ -658,7 +663,7 @@ static int softmax_warps(int L, int per_row_floats) {
 
 extern "C" int sx_softmax_fwd(const float* S, int64_t R, int32_t L, int64_t lds, const float* amax, float clip,
                               float drop_p, uint64_t seed, void* P, int32_t p_dtype, int64_t ldp, int32_t round_tf32,
-                              float* lse, void* stream) {
+                              float* lse, float* diag, void* stream) {
   const int w = softmax_warps(L, 1);
   SX_REQUIRE(w >= 1, "sx_softmax_fwd: row length %d too large", L);
   const size_t smem = (size_t)w * L * 4;
@@ -666,11 +671,11 @@ extern "C" int sx_softmax_fwd(const float* S, int64_t R, int32_t L, int64_t lds,
   if (p_dtype == SX_F32) {
     if (set_smem(softmax_fwd_kernel<float>, smem)) return -2;
     softmax_fwd_kernel<float><<<grid, w * 32, smem, ST(stream)>>>(S, R, L, lds, amax, clip, drop_p, seed, (float*)P, ldp,
-                                                                   lse, round_tf32);
+                                                                   lse, round_tf32, diag);
   } else {
     if (set_smem(softmax_fwd_kernel<__nv_bfloat16>, smem)) return -2;
     softmax_fwd_kernel<__nv_bfloat16><<<grid, w * 32, smem, ST(stream)>>>(S, R, L, lds, amax, clip, drop_p, seed,
-                                                                          (__nv_bfloat16*)P, ldp, lse, 0);
+                                                                          (__nv_bfloat16*)P, ldp, lse, 0, diag);
   }
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -1,0 +1,747 @@
+"""Tensor-level operators of the hot path: thin wrappers that allocate outputs with torch, launch the
+sm_100a kernels through the C ABI on torch's current stream, and wire them into autograd.
+
+PyTorch is used for device memory, streams and the autograd tape only; every arithmetic step below is
+one of the library's own kernels (no ATen math on the path, no fallbacks).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+# ------------------------------------------------------------------------------------------------
+# precision policy
+# ------------------------------------------------------------------------------------------------
+# "tf32": activations/weights stay fp32 in HBM, tensor cores consume them as TF32 (operands pre-rounded
+#         to nearest so the hardware truncation is exact) with fp32 accumulation — parity-grade (<=1e-3).
+_PRECISION = "tf32"
+
+
+def set_precision(p: str):
+    global _PRECISION
+    if p not in ("tf32",):
+        raise ValueError("unsupported precision %r (this build implements 'tf32')" % (p,))
+    _PRECISION = p
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.SxError("segtran_b200 ops need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM on strided views:  C[..., m, n] = epilogue(alpha * sum_k A[..., m, k] B[..., n, k])
+# ------------------------------------------------------------------------------------------------
+def _operand(t: torch.Tensor, Z1: int, Z0: int, name: str) -> L.sx_operand:
+    # t: [z1, z0, R, K] view (batch dims of size 1 broadcast)
+    R, K = t.shape[-2], t.shape[-1]
+    sr, sk = t.stride(-2), t.stride(-1)
+    if sk == 1 or K == 1:
+        major, ld = L.SX_MAJOR_K, sr
+        if R == 1:
+            ld = max(K, 4)
+    elif sr == 1 or R == 1:
+        major, ld = L.SX_MAJOR_MN, sk
+    else:
+        raise L.SxError("gemm operand %s: neither dim is contiguous (strides %s)" % (name, t.stride()))
+    op = L.sx_operand()
+    op.ptr = t.data_ptr()
+    op.major = major
+    op.ld = ld
+    op.stride_z0 = t.stride(1) if t.shape[1] > 1 else 0
+    op.stride_z1 = t.stride(0) if t.shape[0] > 1 else 0
+    return op
+
+
+def _as4(t: torch.Tensor) -> torch.Tensor:
+    while t.dim() < 4:
+        t = t.unsqueeze(0)
+    if t.dim() != 4:
+        raise L.SxError("gemm operands must have <= 4 dims")
+    return t
+
+
+def _pick_split_k(M, N, K, Z, bk=32, sms=148):
+    tiles = ((M + 127) // 128) * ((N + 255) // 256) * Z
+    nkb = (K + bk - 1) // bk
+    if tiles >= sms or nkb < 16:
+        return 1
+    return max(1, min((sms + tiles - 1) // tiles, nkb // 8))
+
+
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, alpha: float = 1.0,
+            bias: Optional[torch.Tensor] = None, bias_mode: int = L.SX_BIAS_N, gelu: bool = False,
+            preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
+            amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
+            reduce_z1: bool = False) -> torch.Tensor:
+    """a [..., M, K], b [..., N, K] (strided fp32 views; either dim may be the contiguous one) ->
+    out [z1, z0, M, N] fp32.  With reduce_z1 the z1 batch dim is summed into one output (atomic accumulate)."""
+    _req_cuda(a, b, out, bias, preact, amax)
+    if a.dtype != torch.float32 or b.dtype != torch.float32:
+        raise L.SxError("gemm_nt: fp32 operands expected (precision policy %s)" % _PRECISION)
+    a4, b4 = _as4(a), _as4(b)
+    M, K = a4.shape[-2:]
+    N, K2 = b4.shape[-2:]
+    if K != K2:
+        raise L.SxError("gemm_nt: K mismatch %d vs %d" % (K, K2))
+    Z1 = max(a4.shape[0], b4.shape[0])
+    Z0 = max(a4.shape[1], b4.shape[1])
+    for t in (a4, b4):
+        if t.shape[0] not in (1, Z1) or t.shape[1] not in (1, Z0):
+            raise L.SxError("gemm_nt: batch dims do not broadcast")
+    oz1 = 1 if reduce_z1 else Z1
+    fresh = out is None
+    linear_epi = (not gelu) and preact is None and drop_p == 0.0 and amax is None
+    if split_k is None:
+        split_k = _pick_split_k(M, N, K, Z0 * Z1) if (linear_epi and (fresh or accumulate or reduce_z1)) else 1
+    if fresh:
+        alloc = torch.zeros if (accumulate or reduce_z1 or split_k > 1) else torch.empty
+        out = alloc((oz1, Z0, M, N), device=a.device, dtype=torch.float32)
+    o4 = _as4(out)
+    if o4.shape[-2:] != (M, N) or o4.stride(-1) != 1:
+        raise L.SxError("gemm_nt: bad output view %s %s" % (tuple(o4.shape), o4.stride()))
+    g = L.sx_gemm_args()
+    g.op_dtype = L.SX_OP_TF32
+    g.M, g.N, g.K, g.Z0, g.Z1 = M, N, K, Z0, Z1
+    g.A = _operand(a4, Z1, Z0, "A")
+    g.B = _operand(b4, Z1, Z0, "B")
+    g.C = o4.data_ptr()
+    g.c_dtype = L.SX_F32
+    g.round_tf32 = 1 if round_out else 0
+    g.ldc = o4.stride(-2)
+    g.c_stride_z0 = o4.stride(1) if o4.shape[1] > 1 else 0
+    g.c_stride_z1 = 0 if reduce_z1 else (o4.stride(0) if o4.shape[0] > 1 else 0)
+    g.alpha = alpha
+    if bias is not None:
+        b4b = bias
+        while b4b.dim() < 3:
+            b4b = b4b.unsqueeze(0)
+        g.bias = bias.data_ptr()
+        g.bias_mode = bias_mode
+        g.bias_stride_z0 = b4b.stride(1) if b4b.shape[1] > 1 else 0
+        g.bias_stride_z1 = b4b.stride(0) if b4b.shape[0] > 1 else 0
+    g.act = L.SX_ACT_GELU if gelu else L.SX_ACT_NONE
+    g.split_k = split_k
+    g.accumulate = 1 if (accumulate or reduce_z1 or split_k > 1) else 0
+    if preact is not None:
+        g.preact = preact.data_ptr()
+    if amax is not None:
+        g.amax = amax.data_ptr()
+    g.drop_p = drop_p
+    g.drop_seed = seed
+    L.call("sx_gemm", C.byref(g), _stream())
+    return out
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def _rowpad_empty(shape, device) -> torch.Tensor:
+    """[..., R, L] view whose row stride is padded to a multiple of 4 floats (TMA needs 16-byte row pitches)."""
+    Lr = shape[-1]
+    buf = torch.empty(tuple(shape[:-1]) + (_pad4(Lr),), device=device, dtype=torch.float32)
+    return buf[..., :Lr]
+
+
+def _rows_ok(t: torch.Tensor) -> bool:
+    """rows contiguous, 16-byte row pitch, and leading dims dense on top of that pitch."""
+    if t.stride(-1) != 1 or t.stride(-2) % 4 != 0 or t.data_ptr() % 16 != 0:
+        return False
+    exp = t.stride(-2) * t.shape[-2]
+    for d in range(t.dim() - 3, -1, -1):
+        if t.shape[d] > 1 and t.stride(d) != exp:
+            return False
+        exp *= t.shape[d]
+    return True
+
+
+def _rowpad(t: torch.Tensor) -> torch.Tensor:
+    if _rows_ok(t):
+        return t
+    o = _rowpad_empty(t.shape, t.device)
+    o.copy_(t)
+    return o
+
+
+def round_tf32(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> fp32 rounded to the nearest TF32 value (weights, once per step)."""
+    _req_cuda(x)
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    L.call("sx_convert", x.data_ptr(), L.SX_F32, x.numel(), y.data_ptr(), L.SX_F32, 1, _stream())
+    return y
+
+
+def colsum(x2d: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[c] += sum_r x2d[r, c] (rows uniformly strided)."""
+    if out is None:
+        out = torch.zeros(x2d.shape[1], device=x2d.device, dtype=torch.float32)
+    L.call("sx_colsum", x2d.data_ptr(), L.SX_F32, x2d.shape[0], x2d.shape[1], x2d.stride(0), out.data_ptr(), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd functions
+# ------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    """y = dropout(act(x W^T + b)).  nn.Linear call sites segtran_shared.py:243, :414, :559-560."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, gelu, drop_p, seed):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        Wr = round_tf32(W)
+        O = W.shape[0]
+        y = torch.empty((x2.shape[0], O), device=x.device, dtype=torch.float32)
+        h = torch.empty_like(y) if gelu else None
+        gemm_nt(x2, Wr, out=y, bias=b, gelu=gelu, preact=h, drop_p=drop_p, seed=seed)
+        ctx.save_for_backward(x2, Wr, h)
+        ctx.meta = (shp, b is not None, gelu, drop_p, seed)
+        return y.view(*shp[:-1], O)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, Wr, h = ctx.saved_tensors
+        shp, has_b, gelu, drop_p, seed = ctx.meta
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        if gelu:
+            dh = torch.empty_like(dy2)
+            L.call("sx_gelu_bwd", dy2.data_ptr(), h.data_ptr(), L.SX_F32, dy2.numel(), drop_p, seed, dh.data_ptr(),
+                   L.SX_F32, 1, _stream())
+            dy2 = dh
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_nt(dy2, Wr.t(), round_out=False).view(shp)
+        if ctx.needs_input_grad[1]:
+            dW = gemm_nt(dy2.t(), x2.t(), round_out=False).view(Wr.shape)
+        if has_b and ctx.needs_input_grad[2]:
+            db = colsum(dy2)
+        return dx, dW, db, None, None, None
+
+
+def linear(x, W, b=None, gelu=False, drop_p=0.0, seed=0):
+    return _Linear.apply(x, W, b, gelu, drop_p, seed)
+
+
+class _AttnScores(torch.autograd.Function):
+    """S[b,m] = scale * Q[b,:,m] K[b,:,m]^T   (segtran_shared.py:566-567); also tracks max(S) on the device.
+    q may have batch 1 (the batch-invariant attractor queries): it is broadcast, and its gradient reduced over b."""
+
+    @staticmethod
+    def forward(ctx, q, k, M, amax):
+        Bq, U1, Cq = q.shape
+        B, U2 = k.shape[0], k.shape[1]
+        d = Cq // M
+        scale = 1.0 / math.sqrt(d)
+        qv = q.view(Bq, U1, M, d).permute(0, 2, 1, 3)         # [Bq,M,U1,d] strided view, d contiguous
+        kv = k.view(B, U2, M, d).permute(0, 2, 1, 3)
+        S = _rowpad_empty((B, M, U1, U2), q.device)
+        gemm_nt(qv, kv, out=S, alpha=scale, amax=amax, round_out=False)
+        ctx.save_for_backward(q, k)
+        ctx.meta = (M, d, scale)
+        return S
+
+    @staticmethod
+    def backward(ctx, dS):
+        q, k = ctx.saved_tensors
+        M, d, scale = ctx.meta
+        Bq, U1, Cq = q.shape
+        B, U2 = k.shape[0], k.shape[1]
+        dS = _rowpad(dS)
+        dq = dk = None
+        if ctx.needs_input_grad[0]:
+            # dQ[b,m] (U1 x d) = scale * dS[b,m] (U1 x U2) . K[b,m] (U2 x d)
+            bcast = Bq == 1 and B > 1
+            dq = torch.zeros_like(q) if bcast else torch.empty_like(q)
+            gemm_nt(dS, k.view(B, U2, M, d).permute(0, 2, 3, 1), out=dq.view(Bq, U1, M, d).permute(0, 2, 1, 3),
+                    alpha=scale, round_out=False, reduce_z1=bcast, split_k=1)
+        if ctx.needs_input_grad[1]:
+            dk = torch.empty_like(k)
+            gemm_nt(dS.transpose(-1, -2), q.view(Bq, U1, M, d).permute(0, 2, 3, 1),
+                    out=dk.view(B, U2, M, d).permute(0, 2, 1, 3), alpha=scale, round_out=False)
+        return dq, dk, None, None
+
+
+class _Softmax(torch.autograd.Function):
+    """P = dropout(softmax(clamp_if(S)))  (segtran_shared.py:578-580, :601-605); output rounded for the P.V GEMM."""
+
+    @staticmethod
+    def forward(ctx, S, amax, clip, drop_p, seed, diag):
+        S = _rowpad(S)
+        Lr, ld = S.shape[-1], S.stride(-2)
+        R = S.numel() // Lr
+        P = _rowpad_empty(S.shape, S.device)
+        lse = torch.empty(R, device=S.device, dtype=torch.float32)
+        L.call("sx_softmax_fwd", S.data_ptr(), R, Lr, ld, _ptr(amax), clip, drop_p, seed, P.data_ptr(), L.SX_F32,
+               P.stride(-2), 1, lse.data_ptr(), _ptr(diag), _stream())
+        ctx.save_for_backward(S, lse, amax)
+        ctx.meta = (clip, drop_p, seed, P.stride(-2))
+        return P
+
+    @staticmethod
+    def backward(ctx, dP):
+        S, lse, amax = ctx.saved_tensors
+        clip, drop_p, seed, ldp = ctx.meta
+        dP = _rowpad(dP)
+        Lr = S.shape[-1]
+        R = S.numel() // Lr
+        dS = _rowpad_empty(S.shape, S.device)
+        L.call("sx_softmax_bwd", dP.data_ptr(), dP.stride(-2), S.data_ptr(), S.stride(-2), lse.data_ptr(), R, Lr,
+               _ptr(amax), clip, drop_p, seed, ldp, dS.data_ptr(), L.SX_F32, dS.stride(-2), 1, _stream())
+        return dS, None, None, None, None, None
+
+
+class _AttnPV(torch.autograd.Function):
+    """U[b,m] = P[b,m] V[b,:,m]   with V [B,U2,M*F], channel = m*F+f  (segtran_shared.py:414-419, :447)."""
+
+    @staticmethod
+    def forward(ctx, P, v, M):
+        B, _, U1, U2 = P.shape
+        Fd = v.shape[-1] // M
+        vv = v.view(B, U2, M, Fd).permute(0, 2, 3, 1)          # [B,M,F,U2]: the "N x K" operand, F contiguous
+        P = _rowpad(P)
+        U = torch.empty((B, M, U1, Fd), device=P.device, dtype=torch.float32)
+        gemm_nt(P, vv, out=U)
+        ctx.save_for_backward(P, v)
+        ctx.meta = (M, Fd)
+        return U
+
+    @staticmethod
+    def backward(ctx, dU):
+        P, v = ctx.saved_tensors
+        M, Fd = ctx.meta
+        B, _, U1, U2 = P.shape
+        dU = dU.contiguous()
+        dP = dv = None
+        if ctx.needs_input_grad[0]:
+            # dP[b,m] (U1 x U2) = dU[b,m] (U1 x F) . V[b,m]^T  -> operand "B" = V[b,m] as [U2, F]
+            dP = _rowpad_empty((B, M, U1, U2), P.device)
+            gemm_nt(dU, v.view(B, U2, M, Fd).permute(0, 2, 1, 3), out=dP, round_out=False)
+        if ctx.needs_input_grad[1]:
+            dv = torch.empty_like(v)
+            # dV[b,m] (U2 x F) = P[b,m]^T (U2 x U1) . dU[b,m] (U1 x F)
+            gemm_nt(P.transpose(-1, -2), dU.transpose(-1, -2), out=dv.view(B, U2, M, Fd).permute(0, 2, 1, 3),
+                    round_out=False)
+        return dP, dv, None
+
+
+class _LayerNorm(torch.autograd.Function):
+    """nn.LayerNorm(C, eps=1e-12, affine) over the last dim (first_norm_layer, segtran_shared.py:456)."""
+
+    @staticmethod
+    def forward(ctx, x, g, b):
+        x = x.contiguous()
+        Cd = x.shape[-1]
+        R = x.numel() // Cd
+        y = torch.empty_like(x)
+        stats = torch.empty((R, 2), device=x.device, dtype=torch.float32)
+        L.call("sx_layernorm_fwd", x.data_ptr(), R, Cd, g.data_ptr(), b.data_ptr(), y.data_ptr(), L.SX_F32, 1,
+               stats.data_ptr(), _stream())
+        ctx.save_for_backward(x, g, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, stats = ctx.saved_tensors
+        dy = dy.contiguous()
+        Cd = x.shape[-1]
+        R = x.numel() // Cd
+        dx = torch.empty_like(x)
+        dg = torch.zeros_like(g)
+        db = torch.zeros_like(g)
+        L.call("sx_layernorm_bwd", dy.data_ptr(), x.data_ptr(), R, Cd, g.data_ptr(), stats.data_ptr(), dx.data_ptr(),
+               L.SX_F32, 1, dg.data_ptr(), db.data_ptr(), _stream())
+        return dx, dg, db
+
+
+class _GroupLinear(torch.autograd.Function):
+    """Y[b,m] = G[b,m] Wo[m]^T + bo[m] — MMPrivateOutput's grouped 1x1 Conv1d (segtran_shared.py:267)."""
+
+    @staticmethod
+    def forward(ctx, G, Wo, bo):
+        B, M, N, Fd = G.shape
+        Wr = round_tf32(Wo.reshape(M, Fd, Fd))
+        Y = torch.empty_like(G)
+        gemm_nt(G, Wr.unsqueeze(0), out=Y, bias=bo.reshape(1, M, Fd), round_out=False)
+        ctx.save_for_backward(G, Wr)
+        ctx.wshape = Wo.shape
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        G, Wr = ctx.saved_tensors
+        B, M, N, Fd = G.shape
+        dY = dY.contiguous()
+        dG = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dG = gemm_nt(dY, Wr.transpose(-1, -2).unsqueeze(0), round_out=False)
+        if ctx.needs_input_grad[1]:
+            dW = gemm_nt(dY.transpose(-1, -2), G.transpose(-1, -2), reduce_z1=True, round_out=False)
+            dW = dW.view(ctx.wshape)
+        if ctx.needs_input_grad[2]:
+            db = torch.zeros((M, Fd), device=G.device, dtype=torch.float32)
+            for bi in range(B):
+                for m in range(M):
+                    colsum(dY[bi, m], out=db[m])
+            db = db.view(-1)
+        return dG, dW, db
+
+
+class _LnSoftAggr(torch.autograd.Function):
+    """out = sum_m softmax_m(Yn_m.ws+bs) Yn_m, Yn = LN(dropout(Y))   (segtran_shared.py:273-274, :318-325)."""
+
+    @staticmethod
+    def forward(ctx, Y, g, b, ws, bs, drop_p, seed):
+        Y = Y.contiguous()
+        B, M, N, Fd = Y.shape
+        out = torch.empty((B, N, Fd), device=Y.device, dtype=torch.float32)
+        stats = torch.empty((B, M, N, 2), device=Y.device, dtype=torch.float32)
+        wts = torch.empty((B, M, N), device=Y.device, dtype=torch.float32)
+        L.call("sx_ln_softaggr_fwd", Y.data_ptr(), B, M, N, Fd, g.data_ptr(), b.data_ptr(), ws.data_ptr(),
+               bs.data_ptr(), drop_p, seed, out.data_ptr(), stats.data_ptr(), wts.data_ptr(), _stream())
+        ctx.save_for_backward(Y, g, b, ws, stats, wts)
+        ctx.meta = (drop_p, seed, bs.shape, ws.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        Y, g, b, ws, stats, wts = ctx.saved_tensors
+        drop_p, seed, bs_shape, ws_shape = ctx.meta
+        B, M, N, Fd = Y.shape
+        dout = dout.contiguous()
+        dY = torch.empty_like(Y)
+        dg = torch.zeros_like(g)
+        db = torch.zeros_like(g)
+        dws = torch.zeros(Fd, device=Y.device, dtype=torch.float32)
+        dbs = torch.zeros(1, device=Y.device, dtype=torch.float32)
+        L.call("sx_ln_softaggr_bwd", dout.data_ptr(), Y.data_ptr(), B, M, N, Fd, g.data_ptr(), b.data_ptr(),
+               ws.data_ptr(), drop_p, seed, stats.data_ptr(), wts.data_ptr(), dY.data_ptr(), L.SX_F32, 1, dg.data_ptr(),
+               db.data_ptr(), dws.data_ptr(), dbs.data_ptr(), _stream())
+        return dY, dg, db, dws.view(ws_shape), dbs.view(bs_shape), None, None
+
+
+class _PosCode(torch.autograd.Function):
+    """LearnedSinuPosEmbedder (segtran_shared.py:989-998) on pos/pos.max() (:1231): [R,pd] -> [R,C0]."""
+
+    @staticmethod
+    def forward(ctx, pos2d, W, b):
+        pos2d = pos2d.contiguous().float()
+        R, pd = pos2d.shape
+        C0 = W.shape[0]
+        pmax = torch.empty(1, device=pos2d.device, dtype=torch.float32)
+        L.call("sx_reduce_max", pos2d.data_ptr(), pos2d.numel(), pmax.data_ptr(), _stream())
+        pe = torch.empty((R, C0), device=pos2d.device, dtype=torch.float32)
+        Wc, bc = W.contiguous(), b.contiguous()
+        L.call("sx_pos_lsinu_fwd", pos2d.data_ptr(), pmax.data_ptr(), R, pd, Wc.data_ptr(), bc.data_ptr(), C0,
+               pe.data_ptr(), _stream())
+        ctx.save_for_backward(pos2d, pmax, Wc, bc)
+        return pe
+
+    @staticmethod
+    def backward(ctx, dpe):
+        pos2d, pmax, W, b = ctx.saved_tensors
+        R, pd = pos2d.shape
+        C0 = W.shape[0]
+        dpe = dpe.contiguous()
+        scratch = torch.empty_like(dpe)
+        dW = torch.zeros_like(W)
+        db = torch.zeros_like(b)
+        L.call("sx_pos_lsinu_bwd", pos2d.data_ptr(), pmax.data_ptr(), R, pd, W.data_ptr(), b.data_ptr(), C0,
+               dpe.data_ptr(), scratch.data_ptr(), dW.data_ptr(), db.data_ptr(), _stream())
+        return None, dW, db
+
+
+class _Prologue(torch.autograd.Function):
+    """h = mask * dropout(LN(LN_{g,b}(x) + posw * pe[:, :C]))   (segtran_shared.py:916, :930-934, :944-946)."""
+
+    @staticmethod
+    def forward(ctx, x, g, b, pe, posw, mask, drop_p, seed):
+        x = x.contiguous()
+        B, N, Cd = x.shape
+        pe = pe.contiguous()                       # [N, C0] shared by the batch, or [B, N, C0]
+        C0 = pe.shape[-1]
+        pe_bstride = 0 if pe.dim() == 2 else N * C0
+        h = torch.empty_like(x)
+        stats = torch.empty((B * N, 4), device=x.device, dtype=torch.float32)
+        L.call("sx_prologue_fwd", x.data_ptr(), B, N, Cd, g.data_ptr(), b.data_ptr(), pe.data_ptr(), C0, pe_bstride,
+               posw, _ptr(mask), drop_p, seed, h.data_ptr(), L.SX_F32, 1, stats.data_ptr(), _stream())
+        ctx.save_for_backward(x, g, b, pe, mask, stats)
+        ctx.meta = (posw, drop_p, seed, pe_bstride)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, g, b, pe, mask, stats = ctx.saved_tensors
+        posw, drop_p, seed, pe_bstride = ctx.meta
+        B, N, Cd = x.shape
+        C0 = pe.shape[-1]
+        dh = dh.contiguous()
+        dx = torch.empty_like(x)
+        dg = torch.zeros_like(g)
+        db = torch.zeros_like(b)
+        dpe = torch.zeros_like(pe) if ctx.needs_input_grad[3] else None
+        L.call("sx_prologue_bwd", dh.data_ptr(), x.data_ptr(), B, N, Cd, g.data_ptr(), b.data_ptr(), pe.data_ptr(), C0,
+               pe_bstride, posw, _ptr(mask), drop_p, seed, stats.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(),
+               _ptr(dpe), _stream())
+        return dx, dg, db, dpe, None, None, None, None
+
+
+class _Transpose(torch.autograd.Function):
+    """[Z,R,C] -> [Z,C,R]: token flatten / scatter (segtran3d.py:328-330, :478-480)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        Z, R, Cd = x.shape
+        y = torch.empty((Z, Cd, R), device=x.device, dtype=torch.float32)
+        L.call("sx_transpose", x.data_ptr(), Z, R, Cd, y.data_ptr(), _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _Transpose.apply(dy)
+
+
+def attn_scores(q, k, M, amax=None):
+    return _AttnScores.apply(q, k, M, amax)
+
+
+def softmax(S, amax=None, clip=500.0, drop_p=0.0, seed=0, diag=None):
+    """diag: optional device float[2] updated in place: [0] = max(diag[0], *amax), [1] += (*amax > clip)."""
+    return _Softmax.apply(S, amax, clip, drop_p, seed, diag)
+
+
+def attn_pv(P, v, M):
+    return _AttnPV.apply(P, v, M)
+
+
+def layer_norm(x, g, b):
+    return _LayerNorm.apply(x, g, b)
+
+
+def group_linear(G, Wo, bo):
+    return _GroupLinear.apply(G, Wo, bo)
+
+
+def ln_softaggr(Y, g, b, ws, bs, drop_p=0.0, seed=0):
+    return _LnSoftAggr.apply(Y, g, b, ws, bs, drop_p, seed)
+
+
+def pos_code(pos2d, W, b):
+    return _PosCode.apply(pos2d, W, b)
+
+
+def prologue(x, g, b, pe, posw, mask, drop_p=0.0, seed=0):
+    return _Prologue.apply(x, g, b, pe, posw, mask, drop_p, seed)
+
+
+def transpose(x):
+    return _Transpose.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# collapsed segmentation head (csrc/sx_head.cu)
+# ------------------------------------------------------------------------------------------------
+def _resize_axis(x: torch.Tensor, axis: int, Lout: int, accumulate_into: Optional[torch.Tensor] = None):
+    shp = list(x.shape)
+    Lin = shp[axis]
+    outer = 1
+    for s in shp[:axis]:
+        outer *= s
+    inner = 1
+    for s in shp[axis + 1:]:
+        inner *= s
+    shp[axis] = Lout
+    if accumulate_into is not None:
+        y = accumulate_into
+        acc = 1
+    else:
+        y = torch.empty(shp, device=x.device, dtype=torch.float32)
+        acc = 0
+    L.call("sx_resize_axis_fwd", x.data_ptr(), outer, Lin, Lout, inner, y.data_ptr(), acc, _stream())
+    return y
+
+
+def _resize_axis_adj(dy: torch.Tensor, axis: int, Lin: int):
+    shp = list(dy.shape)
+    Lout = shp[axis]
+    outer = 1
+    for s in shp[:axis]:
+        outer *= s
+    inner = 1
+    for s in shp[axis + 1:]:
+        inner *= s
+    shp[axis] = Lin
+    dx = torch.empty(shp, device=dy.device, dtype=torch.float32)
+    L.call("sx_resize_axis_bwd", dy.data_ptr(), outer, Lin, Lout, inner, dx.data_ptr(), _stream())
+    return dx
+
+
+class _Resize(torch.autograd.Function):
+    """F.interpolate(x, size, mode='bi/trilinear', align_corners=False) on the trailing dims, one pass per axis."""
+
+    @staticmethod
+    def forward(ctx, x, size):
+        x = x.contiguous()
+        nd = len(size)
+        ctx.in_sizes = tuple(x.shape[-nd:])
+        y = x
+        for i, s in enumerate(size):
+            ax = x.dim() - nd + i
+            if y.shape[ax] != s:
+                y = _resize_axis(y, ax, s)
+        ctx.size = tuple(size)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        nd = len(ctx.size)
+        for i in reversed(range(nd)):
+            ax = dy.dim() - nd + i
+            if ctx.in_sizes[i] != ctx.size[i]:
+                dy = _resize_axis_adj(dy, ax, ctx.in_sizes[i])
+        return dy, None
+
+
+def resize_linear(x, size):
+    return _Resize.apply(x, tuple(int(s) for s in size))
+
+
+def _sgemm(A, B, M, N, K, sa, sb, out=None, alpha=1.0, accumulate=False, Z=1, zs=(0, 0, 0)):
+    """C[z](m,n) (+)= alpha sum_k A[z](m,k) B[z](k,n); sa=(sam,sak), sb=(sbk,sbn); out [Z,M,N] contiguous."""
+    if out is None:
+        out = torch.empty((Z, M, N), device=A.device, dtype=torch.float32)
+    L.call("sx_sgemm_small", A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, sa[0], sa[1], sb[0], sb[1], N, 1, Z,
+           zs[0], zs[1], M * N if zs[2] is None else zs[2], alpha, 1 if accumulate else 0, _stream())
+    return out
+
+
+class _HeadContract(torch.autograd.Function):
+    """L[b,k,v] = sum_c (Wc Wb)[k,c] curr[b,c,v] + (Wc bb + bc)[k] + tvup[b,k,v]
+    with curr [B,Cf,*sp], Wb [F,Cf] (bridge conv), bb [F], Wc [K,F] (class conv), bc [K].
+    Collapsed form of conv_cls(conv_bridge(curr) + up) before interpolation (segtran3d.py:364-367, :488-490)."""
+
+    @staticmethod
+    def forward(ctx, curr, Wb, bb, Wc, bc, tvup):
+        curr = curr.contiguous()
+        B, Cf = curr.shape[:2]
+        V = curr[0, 0].numel()
+        K, Fd = Wc.shape
+        Wb2 = Wb.reshape(Fd, Cf).contiguous() if Wb is not None else None
+        Wc2 = Wc.contiguous()
+        if Wb2 is not None:
+            Wcb = _sgemm(Wc2, Wb2, K, Cf, Fd, (Fd, 1), (Cf, 1))[0]                      # [K,Cf]
+            cc = bc.detach().clone().contiguous() if bc is not None else torch.zeros(K, device=curr.device)
+            _sgemm(Wc2, bb.contiguous(), K, 1, Fd, (Fd, 1), (1, 1), out=cc.view(1, K, 1), accumulate=True)   # += Wc bb
+        else:                                   # bridge conv is nn.Identity (segtran2d.py:177-180): Cf == F
+            Wcb = Wc2
+            cc = bc.contiguous() if bc is not None else torch.zeros(K, device=curr.device)
+        Lo = tvup.contiguous().clone() if tvup is not None else torch.zeros((B, K, V), device=curr.device)
+        L.call("sx_head_contract_fwd", curr.data_ptr(), Wcb.data_ptr(), cc.data_ptr(), B, Cf, V, K, Lo.data_ptr(), 1,
+               _stream())
+        ctx.save_for_backward(curr, Wb2, bb, Wc2, Wcb)
+        ctx.meta = (Wb.shape if Wb is not None else None, tvup is not None, bc is not None)
+        return Lo.view(B, K, *curr.shape[2:])
+
+    @staticmethod
+    def backward(ctx, dL):
+        curr, Wb2, bb, Wc2, Wcb = ctx.saved_tensors
+        wb_shape, has_tv, has_bc = ctx.meta
+        B, Cf = curr.shape[:2]
+        V = curr[0, 0].numel()
+        K, Fd = Wc2.shape
+        dL = dL.contiguous()
+        dcurr = dWb = dbb = dWc = dbc = dtv = None
+        if ctx.needs_input_grad[0]:
+            dcurr = torch.empty_like(curr)
+            L.call("sx_head_contract_bwd_data", dL.data_ptr(), Wcb.data_ptr(), B, Cf, V, K, dcurr.data_ptr(), _stream())
+        dWcb = torch.zeros((K, Cf), device=curr.device, dtype=torch.float32)
+        L.call("sx_head_contract_bwd_weight", dL.data_ptr(), curr.data_ptr(), B, Cf, V, K, dWcb.data_ptr(), _stream())
+        dcc = torch.zeros(K, device=curr.device, dtype=torch.float32)               # d(const)[k] = sum_{b,v} dL
+        L.call("sx_colsum", dL.view(B, K, V).permute(0, 2, 1).reshape(-1, K).contiguous().data_ptr(), L.SX_F32, B * V, K,
+               K, dcc.data_ptr(), _stream())
+        if Wb2 is not None:
+            # Wcb = Wc Wb ; cc = Wc bb + bc
+            dWc = _sgemm(dWcb, Wb2, K, Fd, Cf, (Cf, 1), (1, Cf))[0]                 # dWcb Wb^T   [K,F]
+            dWc = _sgemm(dcc, bb.contiguous(), K, Fd, 1, (1, 1), (1, 1), out=dWc.unsqueeze(0), accumulate=True)[0]
+            dWb = _sgemm(Wc2, dWcb, Fd, Cf, K, (1, Fd), (Cf, 1))[0].reshape(wb_shape)   # Wc^T dWcb  [F,Cf]
+            dbb = _sgemm(Wc2, dcc, Fd, 1, K, (1, Fd), (1, 1))[0].reshape(Fd)           # Wc^T dcc
+        else:
+            dWc = dWcb
+        if has_bc:
+            dbc = dcc
+        if has_tv:
+            dtv = dL.view(B, K, V)
+        return dcurr, dWb, dbb, dWc, dbc, dtv
+
+
+class _TokenClassScores(torch.autograd.Function):
+    """tvT[b,k,n] = sum_f Wc[k,f] vf[b,n,f] — class scores of the fused tokens, channels-first."""
+
+    @staticmethod
+    def forward(ctx, vf, Wc):
+        vf = vf.contiguous()
+        Wc = Wc.contiguous()
+        B, N, Fd = vf.shape
+        K = Wc.shape[0]
+        out = _sgemm(Wc, vf, K, N, Fd, (Fd, 1), (1, Fd), Z=B, zs=(0, N * Fd, K * N))
+        ctx.save_for_backward(vf, Wc)
+        return out
+
+    @staticmethod
+    def backward(ctx, dt):
+        vf, Wc = ctx.saved_tensors
+        B, N, Fd = vf.shape
+        K = Wc.shape[0]
+        dt = dt.contiguous()
+        # dvf[b,n,f] = sum_k dt[b,k,n] Wc[k,f]
+        dvf = _sgemm(dt, Wc, N, Fd, K, (1, N), (Fd, 1), Z=B, zs=(K * N, 0, N * Fd))
+        # dWc[k,f] = sum_{b,n} dt[b,k,n] vf[b,n,f]
+        dWc = torch.zeros((1, K, Fd), device=vf.device, dtype=torch.float32)
+        for bi in range(B):
+            _sgemm(dt[bi], vf[bi], K, Fd, N, (N, 1), (Fd, 1), out=dWc, accumulate=True)
+        return dvf, dWc[0]
+
+
+def seg_head(curr, vfeat_fused, grid, Wb, bb, Wc, bc, out_size, d_pool_k=1, permute_dhw_to_hwd=False):
+    """Collapsed voxel-wise head.  curr [B,Cf,*sp1]; vfeat_fused [B,N,F] tokens on `grid`;
+    3-D: sp1=(D1,H1,W1), depth x d_pool_k, permute to (H,W,D), trilinear to out_size=(H,W,D)  (segtran3d.py:364-496)
+    2-D: sp1=(H1,W1), bilinear to out_size=(H,W)                                              (segtran2d.py:304-436)"""
+    B, N, Fd = vfeat_fused.shape
+    K = Wc.shape[0]
+    Wc2 = Wc.reshape(K, Fd)
+    sp1 = tuple(curr.shape[2:])
+    tv = _TokenClassScores.apply(vfeat_fused, Wc2).view(B, K, *grid)
+    tvup = resize_linear(tv, sp1).reshape(B, K, -1)
+    Lo = _HeadContract.apply(curr, Wb, bb, Wc2, bc, tvup)
+    if len(sp1) == 3:
+        if d_pool_k > 1:
+            Lo = resize_linear(Lo, (sp1[0] * d_pool_k, sp1[1], sp1[2]))
+        H, W, D = out_size
+        Lo = resize_linear(Lo, (D, H, W))                  # same maps as interpolating the (H,W,D)-permuted tensor
+        Dd = Lo.shape[2]
+        out = transpose(Lo.reshape(B * K, Dd, H * W)).view(B, K, H, W, Dd)
+        return out
+    return resize_linear(Lo, tuple(out_size))

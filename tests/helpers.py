@@ -30,3 +30,27 @@ def oracle_encoder(fx, x=None, dtype=torch.float32, collect=None):
     x = fx["x"] if x is None else x
     return O.fusion_encoder(p, "voxel_fusion.", x.to(dtype), fx["voxels_pos"].to(dtype), fx["vmask"], fx["dims"],
                             fx["num_modes"], collect=collect), p
+
+
+def encoder_config(cfg_cls, *, dims, num_modes=4, num_attractors=16, pos_dim=3, qk_have_bias=True, dropout=0.0):
+    """SegtranConfig (reference's or ours) with what Segtran{2d,3d}Config.update_config would derive."""
+    cfg = cfg_cls()
+    cfg.num_translayers = len(dims) - 1
+    cfg.translayer_dims = list(dims)
+    cfg.translayer_compress_ratios = [1] * len(dims)
+    cfg.trans_in_dim, cfg.trans_out_dim, cfg.min_feat_dim = dims[0], dims[-1], min(dims)
+    cfg.num_modes, cfg.num_attractors, cfg.pos_dim, cfg.qk_have_bias = num_modes, num_attractors, pos_dim, qk_have_bias
+    cfg.hidden_dropout_prob = cfg.attention_probs_dropout_prob = dropout
+    return cfg
+
+
+def build_b200_encoder(fx, device="cuda", dropout=0.0):
+    import segtran_b200.networks.segtran_shared as S
+    cfg = encoder_config(S.SegtranConfig, dims=fx["dims"], num_modes=fx["num_modes"],
+                         num_attractors=fx["num_attractors"], pos_dim=fx["pos_dim"], qk_have_bias=fx["qk_have_bias"],
+                         dropout=dropout)
+    enc = S.SegtranFusionEncoder(cfg, "Fusion")
+    init = S.SegtranInitWeights(cfg)
+    enc.apply(init.tie_qk)
+    enc.load_state_dict(fx["state_dict"], strict=True)
+    return enc.to(device)
