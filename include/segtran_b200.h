@@ -152,6 +152,11 @@ int sx_gelu_bwd(const float* dG, const void* H, int32_t h_dtype, int64_t n, floa
 int sx_convert(const void* x, int32_t x_dtype, int64_t n, void* y, int32_t y_dtype, int32_t round_tf32, void* stream);
 /* out[c] += sum_r X[r,c]   (bias gradients) */
 int sx_colsum(const void* X, int32_t x_dtype, int64_t R, int32_t C, int64_t ld, float* out, void* stream);
+/* out[0] += sum_i x[i]*y[i]  and  y = alpha * (*alpha_dev) * x : a linear loss head for benchmarks / checksums */
+int sx_dot(const float* x, const float* y, int64_t n, float* out, void* stream);
+int sx_scale(const float* x, int64_t n, const float* alpha_dev, float alpha, float* y, void* stream);
+/* out[r % out_mod] += sum_c X[r,c]  (class-bias gradient of the head: rows = (batch, class)) */
+int sx_rowsum(const float* X, int64_t R, int64_t C, int64_t ld, int32_t out_mod, float* out, void* stream);
 /* batched transpose [Z,R,C] -> [Z,C,R] fp32: token flatten / scatter (segtran3d.py:328-330, :478-480) */
 int sx_transpose(const float* in, int64_t Z, int32_t R, int32_t C, float* out, void* stream);
 
@@ -165,6 +170,9 @@ int sx_head_contract_bwd_data(const float* dL, const float* W, int32_t B, int32_
                               float* dcurr, void* stream);
 int sx_head_contract_bwd_weight(const float* dL, const float* curr, int32_t B, int32_t Cf, int64_t V, int32_t K,
                                 float* dW, void* stream);
+/* class scores of the fused tokens, exact fp32: out[b,k,n] = sum_f W[k,f] vf[b,n,f]   (Wc . vfeat_fused) */
+int sx_token_scores(const float* vf, const float* W, int32_t B, int32_t N, int32_t F, int32_t K, float* out,
+                    void* stream);
 /* 1-D linear resampling (align_corners=False) of x viewed as [outer, Lin, inner] -> [outer, Lout, inner];
  * F.interpolate(mode='bilinear'|'trilinear') == one pass per axis. */
 int sx_resize_axis_fwd(const float* x, int64_t outer, int32_t Lin, int32_t Lout, int64_t inner, float* y,

@@ -58,9 +58,13 @@ _PROTOS = {
     "sx_convert": [_P, _I, _L, _P, _I, _I, _P],
     "sx_colsum": [_P, _I, _L, _I, _L, _P, _P],
     "sx_transpose": [_P, _L, _I, _I, _P, _P],
+    "sx_dot": [_P, _P, _L, _P, _P],
+    "sx_rowsum": [_P, _L, _L, _L, _I, _P, _P],
+    "sx_scale": [_P, _L, _P, _F, _P, _P],
     "sx_head_contract_fwd": [_P, _P, _P, _I, _I, _L, _I, _P, _I, _P],
     "sx_head_contract_bwd_data": [_P, _P, _I, _I, _L, _I, _P, _P],
     "sx_head_contract_bwd_weight": [_P, _P, _I, _I, _L, _I, _P, _P],
+    "sx_token_scores": [_P, _P, _I, _I, _I, _I, _P, _P],
     "sx_resize_axis_fwd": [_P, _L, _I, _I, _L, _P, _I, _P],
     "sx_resize_axis_bwd": [_P, _L, _I, _I, _L, _P, _P],
     "sx_sgemm_small": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _L, _L, _L, _F, _I, _P],
@@ -96,5 +100,22 @@ def check(rc, what):
         raise SxError("%s failed (rc=%d): %s" % (what, rc, lib().sx_last_error().decode("utf-8", "replace")))
 
 
+# kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
+_LAUNCHES = {"sx_pos_lsinu_bwd": 2, "sx_gemm_debug_set": 0}
+launch_count = 0
+_hook = None          # optional callable(name, args) -> context manager, installed by bench.py for per-kernel timing
+
+
+def set_hook(h):
+    global _hook
+    _hook = h
+
+
 def call(name, *args):
-    check(getattr(lib(), name)(*args), name)
+    global launch_count
+    launch_count += _LAUNCHES.get(name, 1)
+    if _hook is None:
+        check(getattr(lib(), name)(*args), name)
+    else:
+        with _hook(name, args):
+            check(getattr(lib(), name)(*args), name)

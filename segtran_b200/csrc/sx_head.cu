@@ -193,6 +193,31 @@ __global__ void resize_axis_bwd_kernel(const float* __restrict__ dy, long long o
   }
 }
 
+// ---- class scores of the fused tokens, exact fp32: out[b,k,n] = sum_f W[k,f] vf[b,n,f]; one warp per token ----
+__global__ void token_scores_kernel(const float* __restrict__ vf, const float* __restrict__ W, long long T, int N,
+                                    int F, int K, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const float* x = vf + t * F;
+  float acc[MAXK];
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k) acc[k] = 0.f;
+  for (int f = lane; f < F; f += 32) {
+    const float xv = x[f];
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k)
+      if (k < K) acc[k] = fmaf(xv, __ldg(W + (long long)k * F + f), acc[k]);
+  }
+  const long long b = t / N, n = t % N;
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k)
+    if (k < K) {
+      const float s = sx::warp_sum(acc[k]);
+      if (lane == 0) out[(b * K + k) * N + n] = s;
+    }
+}
+
 // ---- tiny strided fp32 GEMM: C[z][m][n] (+)= alpha * sum_k A[z](m,k) B[z](k,n) ----
 __global__ void sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
                                    int M, int N, int K, long long sam, long long sak, long long sbk, long long sbn,
@@ -205,7 +230,18 @@ __global__ void sgemm_small_kernel(const float* __restrict__ A, const float* __r
   const float* a = A + z * saz + (long long)m * sam;
   const float* b = B + z * sbz + (long long)n * sbn;
   float acc = 0.f;
-  for (int k = 0; k < K; ++k) acc = fmaf(a[(long long)k * sak], b[(long long)k * sbk], acc);
+  int k = 0;
+  for (; k + 8 <= K; k += 8) {             // 16 independent loads in flight per thread (latency-bound otherwise)
+    float av[8], bv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      av[u] = a[(long long)(k + u) * sak];
+      bv[u] = b[(long long)(k + u) * sbk];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = fmaf(av[u], bv[u], acc);
+  }
+  for (; k < K; ++k) acc = fmaf(a[(long long)k * sak], b[(long long)k * sbk], acc);
   float* c = C + z * scz + (long long)m * scm + (long long)n * scn;
   *c = accumulate ? *c + alpha * acc : alpha * acc;
 }
@@ -289,6 +325,15 @@ extern "C" int sx_sgemm_small(const float* A, const float* B, float* C, int32_t 
   dim3 blk(32, 8), grid(sx_ceil_div(N, 32), sx_ceil_div(M, 8), Z);
   sgemm_small_kernel<<<grid, blk, 0, ST(stream)>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, scm, scn, saz, sbz, scz, alpha,
                                                    accumulate);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_token_scores(const float* vf, const float* W, int32_t B, int32_t N, int32_t F, int32_t K, float* out,
+                               void* stream) {
+  SX_REQUIRE(K >= 1 && K <= MAXK, "sx_token_scores: num_classes %d not in 1..%d", K, MAXK);
+  const long long T = (long long)B * N;
+  token_scores_kernel<<<sx_ceil_div(T, 8), 256, 0, ST(stream)>>>(vf, W, T, N, F, K, out);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -557,6 +557,47 @@ __global__ void transpose_kernel(const float* __restrict__ in, int R, int C, flo
   }
 }
 
+// out[0] += sum_i x[i] * y[i]     (linear synthetic loss / checksums)
+__global__ void dot_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n, float* out) {
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc = fmaf(x[i], y[i], acc);
+  acc = sx::warp_sum(acc);
+  __shared__ float s[32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
+    acc = sx::warp_sum(acc);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+  }
+}
+
+// out[r % out_mod] += sum_c X[r, c]: one block per row
+__global__ void rowsum_kernel(const float* __restrict__ X, long long C, long long ld, int out_mod, float* out) {
+  const long long r = blockIdx.x;
+  const float* x = X + r * ld;
+  float acc = 0.f;
+  for (long long c = threadIdx.x; c < C; c += blockDim.x) acc += x[c];
+  acc = sx::warp_sum(acc);
+  __shared__ float s[32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
+    acc = sx::warp_sum(acc);
+    if (threadIdx.x == 0) atomicAdd(&out[r % out_mod], acc);
+  }
+}
+
+// y[i] = alpha * x[i]
+__global__ void scale_kernel(const float* __restrict__ x, long long n, const float* __restrict__ alpha_dev, float alpha,
+                             float* __restrict__ y) {
+  const float a = alpha_dev ? alpha * (*alpha_dev) : alpha;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = a * x[i];
+}
+
 int grid_for_rows(long long rows, int per_block, int sms) {
   long long g = (rows + per_block - 1) / per_block;
   long long cap = (long long)sms * 8;
@@ -819,6 +860,25 @@ extern "C" int sx_transpose(const float* in, int64_t Z, int32_t R, int32_t C, fl
   SX_REQUIRE(Z <= 65535, "sx_transpose: batch %lld too large", (long long)Z);
   dim3 grid(sx_ceil_div(C, 32), sx_ceil_div(R, 32), (unsigned)Z), blk(32, 8);
   transpose_kernel<<<grid, blk, 0, ST(stream)>>>(in, R, C, out);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_dot(const float* x, const float* y, int64_t n, float* out, void* stream) {
+  dot_kernel<<<grid_for_rows(n, 256 * 8, sms_cached()), 256, 0, ST(stream)>>>(x, y, n, out);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_scale(const float* x, int64_t n, const float* alpha_dev, float alpha, float* y, void* stream) {
+  scale_kernel<<<grid_for_rows(n, 256 * 8, sms_cached()), 256, 0, ST(stream)>>>(x, n, alpha_dev, alpha, y);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_rowsum(const float* X, int64_t R, int64_t C, int64_t ld, int32_t out_mod, float* out, void* stream) {
+  SX_REQUIRE(R >= 1 && R <= 2147483647ll && out_mod >= 1, "sx_rowsum: bad shape");
+  rowsum_kernel<<<(unsigned)R, 512, 0, ST(stream)>>>(X, C, ld, out_mod, out);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -191,6 +191,40 @@ class Segtran2d(SegtranInitWeights):
             return tuple(f['reduction_%d' % i] for i in range(1, 6))
         return tuple(self.backbone(batch))
 
+    def hot_path(self, feat_fpn, curr_feat, vmask, out_size, B0=None, MOD=0):
+        """The B200 segment: token flatten -> Squeeze-and-Expansion stack -> scatter -> collapsed pixel-wise head
+        (reference segtran2d.py:264-269, :362-436 minus the FPN pyramids).
+        feat_fpn [B,C0,H2,W2], curr_feat [B,Cf,H1,W1], vmask [B,N] or None, out_size = (H,W) -> logits."""
+        B, C0, H2, W2 = feat_fpn.shape
+        B0 = B if B0 is None else B0
+        H, W = out_size
+        vfeat = ops.transpose(feat_fpn.reshape(B, C0, -1))                   # [B,C0,N] -> [B,N,C0]
+        if MOD > 0:
+            vfeat = vfeat.view(B0, MOD, -1, self.trans_in_dim).max(dim=1)[0]
+        grid = torch.Size((H2, W2))
+        sH, sW = H // H2, W // W2
+        if sH * H2 != H or sW * W2 != W:
+            raise ValueError("input size %s is not an integer multiple of the token grid %s" % ((H, W), tuple(grid)))
+        if not self.scales_printed:
+            print("\nImage scales: %dx%d. Feat: %s. Voxels: %s" % (sH, sW, list(grid), list(vfeat.shape)))
+            self.scales_printed = True
+        idx = gen_all_indices(grid, device=vfeat.device).view(-1, 2).float() * \
+            torch.tensor([[float(sH), float(sW)]], device=vfeat.device)
+        voxels_pos = idx.unsqueeze(0).expand(B0, -1, -1)
+        fused = self.voxel_fusion(vfeat, voxels_pos, None if vmask is None else vmask.unsqueeze(2), grid)
+        self.layers_attn_scores = self.voxel_fusion.layers_attn_scores
+        for i in range(self.num_translayers):
+            self.feature_maps.append(self.voxel_fusion.translayers[i].attention_scores)
+        for i in range(self.num_translayers):
+            lv = self.voxel_fusion.layers_vfeat[i]
+            self.feature_maps.append(lv.detach().view(B0, H2, W2, self.translayer_dims[i + 1]).permute(0, 3, 1, 2))
+        self.orig_feat_shape = grid
+        if self.out_fpn_do_dropout and self.training:
+            raise NotImplementedError("segtran_b200: out_fpn_do_dropout breaks the linear head collapse")
+        bridge = self.out_fpn_bridgeconv
+        Wb, bb = (bridge.weight, bridge.bias) if isinstance(bridge, nn.Conv2d) else (None, None)
+        return ops.seg_head(curr_feat, fused, tuple(grid), Wb, bb, self.out_conv.weight, self.out_conv.bias, (H, W))
+
     def forward(self, batch):
         self.feature_maps = []
         MOD = 0
@@ -203,36 +237,9 @@ class Segtran2d(SegtranInitWeights):
         feats = self._backbone_feats(batch)
         cur = self._pyramid(feats, self.in_fpn_layers[:-1], self.in_fpn_convs, self.in_fpn_norms, self.in_fpn_scheme,
                             self.in_fpn_layers[0])
-        cur = self.in_fpn_bridgeconv(cur)
-        H2, W2 = cur.shape[2:]
-        self.feature_maps.append(cur)
-        vfeat = ops.transpose(cur.reshape(B, self.trans_in_dim, -1))         # [B,C0,N] -> [B,N,C0]
-        vmask = nonzero_mask.reshape(B, -1)
-        if self.num_modalities > 0:
-            vfeat = vfeat.view(B0, MOD, -1, self.trans_in_dim).max(dim=1)[0]
-        grid = torch.Size((H2, W2))
-        sH, sW = H // H2, W // W2
-        if sH * H2 != H or sW * W2 != W:
-            raise ValueError("input size %s is not an integer multiple of the token grid %s" % ((H, W), tuple(grid)))
-        if not self.scales_printed:
-            print("\nImage scales: %dx%d. Feat: %s. Voxels: %s" % (sH, sW, list(grid), list(vfeat.shape)))
-            self.scales_printed = True
-        idx = gen_all_indices(grid, device=vfeat.device).view(-1, 2).float() * \
-            torch.tensor([[float(sH), float(sW)]], device=vfeat.device)
-        voxels_pos = idx.unsqueeze(0).expand(B0, -1, -1)
-        fused = self.voxel_fusion(vfeat, voxels_pos, vmask.unsqueeze(2), grid)
-        self.layers_attn_scores = self.voxel_fusion.layers_attn_scores
-        for i in range(self.num_translayers):
-            self.feature_maps.append(self.voxel_fusion.translayers[i].attention_scores)
-        for i in range(self.num_translayers):
-            lv = self.voxel_fusion.layers_vfeat[i]
-            self.feature_maps.append(lv.detach().view(B0, H2, W2, self.translayer_dims[i + 1]).permute(0, 3, 1, 2))
-        self.orig_feat_shape = grid
+        feat_fpn = self.in_fpn_bridgeconv(cur)
+        self.feature_maps.append(feat_fpn)
         layers = self.out_fpn_layers[:-len(self.in_fpn_layers)]
-        curr = self._pyramid(feats, layers, self.out_fpn_convs, self.out_fpn_norms, self.out_fpn_scheme,
-                             self.out_fpn_layers[0])
-        if self.out_fpn_do_dropout and self.training:
-            raise NotImplementedError("segtran_b200: out_fpn_do_dropout breaks the linear head collapse")
-        bridge = self.out_fpn_bridgeconv
-        Wb, bb = (bridge.weight, bridge.bias) if isinstance(bridge, nn.Conv2d) else (None, None)
-        return ops.seg_head(curr, fused, tuple(grid), Wb, bb, self.out_conv.weight, self.out_conv.bias, (H, W))
+        curr_feat = self._pyramid(feats, layers, self.out_fpn_convs, self.out_fpn_norms, self.out_fpn_scheme,
+                                  self.out_fpn_layers[0])
+        return self.hot_path(feat_fpn, curr_feat, nonzero_mask.reshape(B, -1), (H, W), B0, MOD)

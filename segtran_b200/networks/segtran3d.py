@@ -207,6 +207,7 @@ class Segtran3d(SegtranInitWeights):
         return cur
 
     def in_fpn_forward(self, batch_base_feats, nonzero_mask):
+        """In-FPN pyramid + depth pooling (stock ops): -> feat_fpn [B,C0,D2,H2,W2], vmask [B,N]."""
         cur = self._pyramid(batch_base_feats, self.in_fpn_layers[:-1], self.in_fpn_convs, self.in_fpn_norms,
                             self.in_fpn_scheme, self.in_fpn_layers[0])
         cur = self.in_fpn_bridgeconv(cur)
@@ -215,19 +216,39 @@ class Segtran3d(SegtranInitWeights):
         cur = F.interpolate(cur, size=size, mode='trilinear', align_corners=False)
         m = F.interpolate(nonzero_mask.float().unsqueeze(1), size=size, mode='trilinear', align_corners=False)
         vmask = (m.squeeze(1) >= 0.5).long().reshape(cur.shape[0], -1)
-        B, C0, D2, H2, W2 = cur.shape
-        vfeat = ops.transpose(cur.reshape(B, C0, -1))                 # [B,C0,N] -> [B,N,C0]  (flatten kernel)
-        return vfeat, vmask, D2, H2, W2
+        return cur, vmask
 
-    def out_fpn_forward(self, batch_base_feats, vfeat_fused_tokens, grid, out_size):
-        """Out-FPN pyramid (stock ops) followed by the collapsed head; returns the full-size logits directly."""
+    def out_fpn_pyramid(self, batch_base_feats):
+        """Out-FPN pyramid (stock ops): -> curr_feat [B,Cf,D1,H1,W1], the head's dense input."""
         layers = self.out_fpn_layers[:-len(self.in_fpn_layers)]
-        cur = self._pyramid(batch_base_feats, layers, self.out_fpn_convs, self.out_fpn_norms, self.out_fpn_scheme,
-                            self.out_fpn_layers[0])
+        return self._pyramid(batch_base_feats, layers, self.out_fpn_convs, self.out_fpn_norms, self.out_fpn_scheme,
+                             self.out_fpn_layers[0])
+
+    def hot_path(self, feat_fpn, curr_feat, vmask, out_size):
+        """The B200 segment of the forward: token flatten -> Squeeze-and-Expansion stack -> scatter -> collapsed
+        voxel-wise head (reference segtran3d.py:326-332, :442-498 minus the FPN pyramids).
+        feat_fpn [B,C0,D2,H2,W2], curr_feat [B,Cf,D1,H1,W1], vmask [B,N] or None, out_size = (H,W,D) -> logits."""
+        B, C0, D2, H2, W2 = feat_fpn.shape
+        H, W, D = out_size
+        grid = torch.Size((D2, H2, W2))
+        sH, sW, sD = H // H2, W // W2, D // D2                        # D: depth of the original volume (reference :446)
+        if sH * H2 != H or sW * W2 != W or sD * D2 != D:
+            raise ValueError("input size %s is not an integer multiple of the token grid %s" % ((H, W, D), tuple(grid)))
+        vfeat = ops.transpose(feat_fpn.reshape(B, C0, -1))            # [B,C0,N] -> [B,N,C0]  (flatten kernel)
+        scale = [sD / self.input_scale[2], sH / self.input_scale[0], sW / self.input_scale[1]]
+        if not self.scales_printed:
+            print("\nFeat: %s, Voxels: %s. Model DHW scales: %dx%dx%d. Total scales: %s" %
+                  (list(grid), list(vfeat.shape), sD, sH, sW, scale))
+            self.scales_printed = True
+        idx = gen_all_indices(grid, device=vfeat.device).view(-1, 3).float() * torch.tensor([scale], device=vfeat.device)
+        voxels_pos = idx.unsqueeze(0).expand(B, -1, -1)               # one set of positions, shared by the batch
+        fused = self.voxel_fusion(vfeat, voxels_pos, None if vmask is None else vmask.unsqueeze(2), grid)
+        self.layers_attn_scores = self.voxel_fusion.layers_attn_scores
+        self.orig_feat_shape = grid
         if self.out_fpn_do_dropout and self.training:
             raise NotImplementedError("segtran_b200: out_fpn_do_dropout breaks the linear head collapse")
         dk = self.D_pool_K if (self.D_pool_K > 1 and self.out_fpn_upsampleD_scheme == 'interp') else 1
-        return ops.seg_head(cur, vfeat_fused_tokens, grid, self.out_fpn_bridgeconv3d.weight,
+        return ops.seg_head(curr_feat, fused, tuple(grid), self.out_fpn_bridgeconv3d.weight,
                             self.out_fpn_bridgeconv3d.bias, self.out_conv3d.weight, self.out_conv3d.bias, out_size,
                             d_pool_k=dk)
 
@@ -244,19 +265,6 @@ class Segtran3d(SegtranInitWeights):
         nonzero_mask = self.get_mask(x)
         f = self.backbone.extract_features(x)
         feats = tuple(f[k] for k in _I3D_KEYS)
-        vfeat, vmask, D2, H2, W2 = self.in_fpn_forward(feats, nonzero_mask)
-        grid = torch.Size((D2, H2, W2))
-        sH, sW, sD = H // H2, W // W2, D // D2                        # D: depth of the original volume (reference :446)
-        if sH * H2 != H or sW * W2 != W or sD * D2 != D:
-            raise ValueError("input size %s is not an integer multiple of the token grid %s" % ((H, W, D), tuple(grid)))
-        scale = [sD / self.input_scale[2], sH / self.input_scale[0], sW / self.input_scale[1]]
-        if not self.scales_printed:
-            print("\nFeat: %s, Voxels: %s. Model DHW scales: %dx%dx%d. Total scales: %s" %
-                  (list(grid), list(vfeat.shape), sD, sH, sW, scale))
-            self.scales_printed = True
-        idx = gen_all_indices(grid, device=vfeat.device).view(-1, 3).float() * torch.tensor([scale], device=vfeat.device)
-        voxels_pos = idx.unsqueeze(0).expand(B, -1, -1)               # one set of positions, shared by the batch
-        fused = self.voxel_fusion(vfeat, voxels_pos, vmask.unsqueeze(2), grid)
-        self.layers_attn_scores = self.voxel_fusion.layers_attn_scores
-        self.orig_feat_shape = grid
-        return self.out_fpn_forward(feats, fused, tuple(grid), (H, W, D))
+        feat_fpn, vmask = self.in_fpn_forward(feats, nonzero_mask)
+        curr_feat = self.out_fpn_pyramid(feats)
+        return self.hot_path(feat_fpn, curr_feat, vmask, (H, W, D))

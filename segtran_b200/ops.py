@@ -523,6 +523,31 @@ class _Transpose(torch.autograd.Function):
         return _Transpose.apply(dy)
 
 
+class _Dot(torch.autograd.Function):
+    """loss = sum(x * w) for a fixed weight tensor w (a linear stand-in for the training loss in benchmarks)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x = x.contiguous()
+        out = torch.zeros(1, device=x.device, dtype=torch.float32)
+        L.call("sx_dot", x.data_ptr(), w.data_ptr(), x.numel(), out.data_ptr(), _stream())
+        ctx.save_for_backward(w)
+        ctx.shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        dx = torch.empty_like(w)
+        g = g.contiguous()
+        L.call("sx_scale", w.data_ptr(), w.numel(), g.data_ptr(), 1.0, dx.data_ptr(), _stream())
+        return dx.view(ctx.shape), None
+
+
+def dot(x, w):
+    return _Dot.apply(x, w.contiguous())
+
+
 def attn_scores(q, k, M, amax=None):
     return _AttnScores.apply(q, k, M, amax)
 
@@ -677,15 +702,16 @@ class _HeadContract(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dcurr = torch.empty_like(curr)
             L.call("sx_head_contract_bwd_data", dL.data_ptr(), Wcb.data_ptr(), B, Cf, V, K, dcurr.data_ptr(), _stream())
-        dWcb = torch.zeros((K, Cf), device=curr.device, dtype=torch.float32)
-        L.call("sx_head_contract_bwd_weight", dL.data_ptr(), curr.data_ptr(), B, Cf, V, K, dWcb.data_ptr(), _stream())
+        # dWcb[k,c] = sum_{b,v} dL[b,k,v] curr[b,c,v]: a (K x Cf x B*V) product streamed once through the tensor
+        # cores (TF32 operands, fp32 accumulation; HBM-bound on reading curr), reduced over the batch atomically
+        dWcb = gemm_nt(dL.view(B, 1, K, V), curr.view(B, 1, Cf, V), reduce_z1=True, round_out=False).view(K, Cf)
         dcc = torch.zeros(K, device=curr.device, dtype=torch.float32)               # d(const)[k] = sum_{b,v} dL
-        L.call("sx_colsum", dL.view(B, K, V).permute(0, 2, 1).reshape(-1, K).contiguous().data_ptr(), L.SX_F32, B * V, K,
-               K, dcc.data_ptr(), _stream())
+        L.call("sx_rowsum", dL.data_ptr(), B * K, V, V, K, dcc.data_ptr(), _stream())
         if Wb2 is not None:
             # Wcb = Wc Wb ; cc = Wc bb + bc
-            dWc = _sgemm(dWcb, Wb2, K, Fd, Cf, (Cf, 1), (1, Cf))[0]                 # dWcb Wb^T   [K,F]
-            dWc = _sgemm(dcc, bb.contiguous(), K, Fd, 1, (1, 1), (1, 1), out=dWc.unsqueeze(0), accumulate=True)[0]
+            dWc = gemm_nt(dWcb, Wb2, round_out=False).view(1, K, Fd)                  # dWcb Wb^T   [K,F]
+            _sgemm(dcc, bb.contiguous(), K, Fd, 1, (1, 1), (1, 1), out=dWc, accumulate=True)
+            dWc = dWc[0]
             dWb = _sgemm(Wc2, dWcb, Fd, Cf, K, (1, Fd), (Cf, 1))[0].reshape(wb_shape)   # Wc^T dWcb  [F,Cf]
             dbb = _sgemm(Wc2, dcc, Fd, 1, K, (1, Fd), (1, 1))[0].reshape(Fd)           # Wc^T dcc
         else:
@@ -706,7 +732,8 @@ class _TokenClassScores(torch.autograd.Function):
         Wc = Wc.contiguous()
         B, N, Fd = vf.shape
         K = Wc.shape[0]
-        out = _sgemm(Wc, vf, K, N, Fd, (Fd, 1), (1, Fd), Z=B, zs=(0, N * Fd, K * N))
+        out = torch.empty((B, K, N), device=vf.device, dtype=torch.float32)
+        L.call("sx_token_scores", vf.data_ptr(), Wc.data_ptr(), B, N, Fd, K, out.data_ptr(), _stream())   # exact fp32
         ctx.save_for_backward(vf, Wc)
         return out
 
@@ -716,13 +743,18 @@ class _TokenClassScores(torch.autograd.Function):
         B, N, Fd = vf.shape
         K = Wc.shape[0]
         dt = dt.contiguous()
-        # dvf[b,n,f] = sum_k dt[b,k,n] Wc[k,f]
+        # dvf[b,n,f] = sum_k dt[b,k,n] Wc[k,f]      (K = num_classes: CUDA-core product, coalesced over f)
         dvf = _sgemm(dt, Wc, N, Fd, K, (1, N), (Fd, 1), Z=B, zs=(K * N, 0, N * Fd))
-        # dWc[k,f] = sum_{b,n} dt[b,k,n] vf[b,n,f]
-        dWc = torch.zeros((1, K, Fd), device=vf.device, dtype=torch.float32)
-        for bi in range(B):
-            _sgemm(dt[bi], vf[bi], K, Fd, N, (N, 1), (Fd, 1), out=dWc, accumulate=True)
-        return dvf, dWc[0]
+        # dWc[k,f] = sum_{b,n} dt[b,k,n] vf[b,n,f]  (tensor cores, reduced over the batch)
+        if N % 4 == 0:
+            dWc = gemm_nt(dt.view(B, 1, K, N), vf.transpose(1, 2).unsqueeze(1), reduce_z1=True, round_out=False)
+            dWc = dWc.view(K, Fd)
+        else:
+            dWc = torch.zeros((1, K, Fd), device=vf.device, dtype=torch.float32)
+            for bi in range(B):
+                _sgemm(dt[bi], vf[bi], K, Fd, N, (N, 1), (Fd, 1), out=dWc, accumulate=True)
+            dWc = dWc[0]
+        return dvf, dWc
 
 
 def seg_head(curr, vfeat_fused, grid, Wb, bb, Wc, bc, out_size, d_pool_k=1, permute_dhw_to_hwd=False):

@@ -1,0 +1,83 @@
+"""Data-parallel gradient exchange for the hot path: one flat fp32 bucket, one NCCL all-reduce per step.
+
+The reference wraps the whole model in DistributedDataParallel with find_unused_parameters=True
+(train3d.py:671-676, train2d.py:1108-1113).  The Squeeze-and-Expansion path itself is per-sample, so the only
+collective it needs is the mean of the parameter gradients over ranks.  ``GradBucket`` makes every parameter's
+``.grad`` a view into ONE contiguous buffer (so no gather/scatter copies are needed), skips the parameters the
+reference constructs but never uses (their .grad stays zero — same result as DDP's unused-parameter handling),
+and issues a single all-reduce over NVLink/NVSwitch on a side stream.
+
+Backend: NCCL on GPUs (one process per GPU, ``torch.distributed``); the same code runs on gloo for the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+import torch.distributed as dist
+
+
+class GradBucket:
+    def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None):
+        seen, self.params = set(), []
+        for p in params:                      # tied parameters (query/key) appear once
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                self.params.append(p)
+        if not self.params:
+            raise ValueError("GradBucket: no trainable parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)      # autograd accumulates in place into the bucket
+            off += n
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self._comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._work = None
+
+    def zero(self):
+        """Replaces optimizer.zero_grad(): one memset instead of one per parameter; .grad views stay attached."""
+        self.flat.zero_()
+
+    def reattach(self):
+        """Call if something replaced p.grad (e.g. zero_grad(set_to_none=True))."""
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.flat[off:off + n].data_ptr():
+                p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def allreduce_async(self):
+        """Average the bucket over ranks; returns immediately (the transfer runs on a side stream on GPUs)."""
+        if self.world == 1:
+            return
+        if self._comm is not None:
+            self._comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm):
+                self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self._scaled = False
+        else:
+            self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._scaled = False
+
+    def wait(self):
+        """Make the averaged gradients visible to the current stream (call before the optimizer step)."""
+        if self.world == 1 or self._work is None:
+            return
+        if self._comm is not None:
+            with torch.cuda.stream(self._comm):
+                self._work.wait()
+                self.flat.mul_(1.0 / self.world)
+            torch.cuda.current_stream().wait_stream(self._comm)
+        else:
+            self._work.wait()
+            self.flat.mul_(1.0 / self.world)
+        self._work = None
+
+    def bytes(self) -> int:
+        return self.numel * self.flat.element_size()
