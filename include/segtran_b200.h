@@ -114,7 +114,8 @@ int sx_prologue_fwd(const float* x, int64_t B, int32_t N, int32_t C, const float
 /* dh fp32 -> dx [B,N,C]; dg, db [C] and dpe (same addressing as pe, may be NULL) are accumulated (+=). */
 int sx_prologue_bwd(const float* dh, const float* x, int64_t B, int32_t N, int32_t C, const float* g, const float* b,
                     const float* pe, int32_t C0, int64_t pe_bstride, float posw, const float* mask, float drop_p,
-                    uint64_t seed, const float* stats, float* dx, float* dg, float* db, float* dpe, void* stream);
+                    uint64_t seed, const float* stats, float* dx, float* dg, float* db, float* dpe,
+                    float* dt_scratch /* [B*N*C] or NULL */, void* stream);
 
 /* Row softmax with the reference's conditional clamp and attention dropout (segtran_shared.py:578-580, :601-605):
  *   if (*amax > clip) S = clamp(S, -clip, clip);  P = dropout(softmax(S)).  S [R,L] fp32 (row stride lds),
@@ -143,7 +144,7 @@ int sx_ln_softaggr_fwd(const float* Y, int32_t B, int32_t M, int32_t N, int32_t 
 int sx_ln_softaggr_bwd(const float* dout, const float* Y, int32_t B, int32_t M, int32_t N, int32_t F, const float* g,
                        const float* b, const float* ws, float drop_p, uint64_t seed, const float* stats,
                        const float* wts, void* dY, int32_t dy_dtype, int32_t round_tf32, float* dg, float* db,
-                       float* dws, float* dbs, void* stream);
+                       float* dws, float* dbs, float* dscore_scratch /* [B*M*N] or NULL */, void* stream);
 
 /* dH = dropout'(dG) * gelu'(H)  (MMSharedMid backward, segtran_shared.py:243-245) */
 int sx_gelu_bwd(const float* dG, const void* H, int32_t h_dtype, int64_t n, float drop_p, uint64_t seed, void* dH,
@@ -155,6 +156,9 @@ int sx_colsum(const void* X, int32_t x_dtype, int64_t R, int32_t C, int64_t ld, 
 /* out[0] += sum_i x[i]*y[i]  and  y = alpha * (*alpha_dev) * x : a linear loss head for benchmarks / checksums */
 int sx_dot(const float* x, const float* y, int64_t n, float* out, void* stream);
 int sx_scale(const float* x, int64_t n, const float* alpha_dev, float alpha, float* y, void* stream);
+/* out[z0][c] += sum_{z1,r} X[z1][z0][r][c]  (per-mode bias gradient of MMPrivateOutput in one launch) */
+int sx_colsum_batched(const float* X, int32_t Z1, int64_t stride_z1, int32_t Z0, int64_t stride_z0, int64_t R, int32_t C,
+                      int64_t ld, float* out, void* stream);
 /* out[r % out_mod] += sum_c X[r,c]  (class-bias gradient of the head: rows = (batch, class)) */
 int sx_rowsum(const float* X, int64_t R, int64_t C, int64_t ld, int32_t out_mod, float* out, void* stream);
 /* batched transpose [Z,R,C] -> [Z,C,R] fp32: token flatten / scatter (segtran3d.py:328-330, :478-480) */

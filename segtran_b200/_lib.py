@@ -47,17 +47,18 @@ _PROTOS = {
     "sx_pos_lsinu_fwd": [_P, _P, _L, _I, _P, _P, _I, _P, _P],
     "sx_pos_lsinu_bwd": [_P, _P, _L, _I, _P, _P, _I, _P, _P, _P, _P, _P],
     "sx_prologue_fwd": [_P, _L, _I, _I, _P, _P, _P, _I, _L, _F, _P, _F, _U64, _P, _I, _I, _P, _P],
-    "sx_prologue_bwd": [_P, _P, _L, _I, _I, _P, _P, _P, _I, _L, _F, _P, _F, _U64, _P, _P, _P, _P, _P, _P],
+    "sx_prologue_bwd": [_P, _P, _L, _I, _I, _P, _P, _P, _I, _L, _F, _P, _F, _U64, _P, _P, _P, _P, _P, _P, _P],
     "sx_softmax_fwd": [_P, _L, _I, _L, _P, _F, _F, _U64, _P, _I, _L, _I, _P, _P, _P],
     "sx_softmax_bwd": [_P, _L, _P, _L, _P, _L, _I, _P, _F, _F, _U64, _L, _P, _I, _L, _I, _P],
     "sx_layernorm_fwd": [_P, _L, _I, _P, _P, _P, _I, _I, _P, _P],
     "sx_layernorm_bwd": [_P, _P, _L, _I, _P, _P, _P, _I, _I, _P, _P, _P],
     "sx_ln_softaggr_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _F, _U64, _P, _P, _P, _P],
-    "sx_ln_softaggr_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _U64, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
+    "sx_ln_softaggr_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _U64, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P],
     "sx_gelu_bwd": [_P, _P, _I, _L, _F, _U64, _P, _I, _I, _P],
     "sx_convert": [_P, _I, _L, _P, _I, _I, _P],
     "sx_colsum": [_P, _I, _L, _I, _L, _P, _P],
     "sx_transpose": [_P, _L, _I, _I, _P, _P],
+    "sx_colsum_batched": [_P, _I, _L, _I, _L, _L, _I, _L, _P, _P],
     "sx_dot": [_P, _P, _L, _P, _P],
     "sx_rowsum": [_P, _L, _L, _L, _I, _P, _P],
     "sx_scale": [_P, _L, _P, _F, _P, _P],
@@ -101,7 +102,7 @@ def check(rc, what):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
-_LAUNCHES = {"sx_pos_lsinu_bwd": 2, "sx_gemm_debug_set": 0}
+_LAUNCHES = {"sx_pos_lsinu_bwd": 2, "sx_ln_softaggr_bwd": 2, "sx_prologue_bwd": 3, "sx_layernorm_bwd": 2, "sx_gemm_debug_set": 0}
 launch_count = 0
 _hook = None          # optional callable(name, args) -> context manager, installed by bench.py for per-kernel timing
 

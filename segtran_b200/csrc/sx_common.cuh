@@ -178,13 +178,28 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
-// counter-based uniform in [0,1): splitmix64 of (seed, index)
-__device__ __forceinline__ float uniform_hash(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+// Counter-based dropout bits: one 64-bit hash per group of 4 consecutive elements (index >> 2), 16 bits per
+// element; keep(idx) <=> field(idx & 3) >= p16 with p16 = round(p * 65536).  Two rounds of a 32-bit avalanche
+// mixer (lowbias32) keyed by the seed: ~5 integer ops per element, so the mask can be regenerated in backward for free.
+__device__ __forceinline__ uint32_t drop_p16(float p) {
+  const float v = p * 65536.f + 0.5f;
+  return v >= 65535.f ? 65535u : (uint32_t)v;
+}
+__device__ __forceinline__ uint2 drop_hash(unsigned long long seed, unsigned long long idx4) {
+  uint32_t a = (uint32_t)idx4 * 0x9E3779B1u ^ (uint32_t)seed;
+  a ^= (uint32_t)(idx4 >> 32) * 0x85EBCA77u;
+  a ^= a >> 16; a *= 0x7FEB352Du; a ^= a >> 15; a *= 0x846CA68Bu; a ^= a >> 16;
+  uint32_t b = a ^ (uint32_t)(seed >> 32) ^ 0x68E31DA4u;
+  b ^= b >> 16; b *= 0x21F0AAADu; b ^= b >> 15; b *= 0x735A2D97u; b ^= b >> 15;
+  return make_uint2(a, b);
+}
+__device__ __forceinline__ bool drop_keep(uint2 h, int j, uint32_t p16) {
+  const uint32_t w = (j & 2) ? h.y : h.x;
+  return ((w >> ((j & 1) * 16)) & 0xFFFFu) >= p16;
+}
+// scalar form (any alignment)
+__device__ __forceinline__ bool drop_keep1(unsigned long long seed, unsigned long long idx, uint32_t p16) {
+  return drop_keep(drop_hash(seed, idx >> 2), (int)(idx & 3), p16);
 }
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   // valid for any sign mix: order-preserving int compare

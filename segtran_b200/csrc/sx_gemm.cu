@@ -31,7 +31,9 @@ constexpr int B_STAGE_BYTES = BN * BKB;       // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STG_LD = 36;                   // staging row pitch in floats (16-byte aligned, conflict-free quarter-warps)
+constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;   // one [32][36] fp32 tile per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STG_BYTES;
 
 struct GemmParams {
   int M, N, K, Z0, Z1;
@@ -90,6 +92,7 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]       MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]     epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* stage_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -208,9 +211,61 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // TMEM -> registers (one accumulator row per thread) -> bias/act/dropout/rounding -> per-warp shared-memory
+    // staging tile [32 rows][32 cols] -> row-contiguous global stores: every warp store instruction writes four
+    // full 128-byte row segments instead of 32 scattered 16-byte pieces.
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    float* stg = stage_base + q * (32 * STG_LD);
     int it = 0;
     float tmax = -3.0e38f;
+    const int sr = lane >> 3, sc = (lane & 7) * 4;      // cooperative-store coordinates inside the staging tile
+
+    auto coop_store = [&](void* base, const float (&f)[32], long long zoff, int row0, int col0, bool atomic_add) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stg + lane * STG_LD + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int rr = 0; rr < 32; rr += 4) {
+        const int r = rr + sr;
+        const int grow = row0 + r;
+        const int col = col0 + sc;
+        if (grow < p.M && col < p.N) {
+          const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_LD + sc);
+          const long long off = zoff + (long long)grow * p.ldc + col;
+          const bool full4 = (col + 3 < p.N) && p.c_vec_ok;
+          if (p.c_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(base) + off;
+            if (full4) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(o) = pk;
+            } else {
+              const float e[4] = {v.x, v.y, v.z, v.w};
+              for (int u = 0; u < 4; ++u)
+                if (col + u < p.N) o[u] = __float2bfloat16_rn(e[u]);
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(base) + off;
+            if (atomic_add) {
+              const float e[4] = {v.x, v.y, v.z, v.w};
+              for (int u = 0; u < 4; ++u)
+                if (col + u < p.N) atomicAdd(o + u, e[u]);
+            } else if (full4) {
+              *reinterpret_cast<float4*>(o) = v;
+            } else {
+              const float e[4] = {v.x, v.y, v.z, v.w};
+              for (int u = 0; u < 4; ++u)
+                if (col + u < p.N) o[u] = e[u];
+            }
+          }
+        }
+      }
+      __syncwarp();
+    };
+
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int z0, z1, mb, nb, ks;
       decode(t, z0, z1, mb, nb, ks);
@@ -218,7 +273,8 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t acc_phase = (it >> 1) & 1;
       sx::mbar_wait(&tfull_bar[acc], acc_phase);
       sx::tc_fence_after();
-      const int row = mb * BM + q * 32 + lane;
+      const int row0 = mb * BM + q * 32;
+      const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const long long zoff = (long long)z1 * p.c_sz1 + (long long)z0 * p.c_sz0;
       const long long roff = zoff + (long long)row * p.ldc;
@@ -233,88 +289,45 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[32];
         sx::tmem_ld32(taddr + c * 32, v);
         sx::tmem_ld_wait();
-        if (row_ok) {
-          float f[32];
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) * p.alpha + bias_m;
-            if (add_bias && p.bias_mode == SX_BIAS_N && col0 + j < p.N) x += bias[col0 + j];
-            f[j] = x;
-          }
-          const bool full = (col0 + 32 <= p.N) && p.c_vec_ok;
-          if (p.preact) {
-            if (p.c_bf16) {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.preact) + roff + col0;
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) o[j] = __float2bfloat16_rn(f[j]);
-            } else {
-              float* o = reinterpret_cast<float*>(p.preact) + roff + col0;
-              if (full) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha + bias_m;
+        if (add_bias && p.bias_mode == SX_BIAS_N) {
+          const float bj = (col0 + lane < p.N) ? bias[col0 + lane] : 0.f;     // one coalesced load, then broadcast
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.N) o[j] = f[j];
-              }
-            }
-          }
-          if (p.act == SX_ACT_GELU) {
+          for (int j = 0; j < 32; ++j) f[j] += __shfl_sync(0xffffffffu, bj, j);
+        }
+        if (p.preact) coop_store(p.preact, f, zoff, row0, col0, false);
+        if (p.act == SX_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = sx::gelu_erf(f[j]);
-          }
-          if (p.drop_p > 0.f) {
-            const float keep_scale = 1.f / (1.f - p.drop_p);
+          for (int j = 0; j < 32; ++j) f[j] = sx::gelu_erf(f[j]);
+        }
+        if (p.drop_p > 0.f) {
+          const float keep_scale = 1.f / (1.f - p.drop_p);
+          const uint32_t p16 = sx::drop_p16(p.drop_p);
+          const unsigned long long e0 = (unsigned long long)(roff + col0);
+          if ((e0 & 3ull) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float u = sx::uniform_hash(p.drop_seed, (unsigned long long)(roff + col0 + j));
-              f[j] = (u >= p.drop_p) ? f[j] * keep_scale : 0.f;
-            }
-          }
-          if (p.round_tf32 && !p.c_bf16) {
+            for (int j = 0; j < 32; j += 4) {
+              const uint2 h = sx::drop_hash(p.drop_seed, (e0 + j) >> 2);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = sx::round_tf32(f[j]);
-          }
-          if (p.amax) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) tmax = fmaxf(tmax, f[j]);
-          }
-          if (p.c_bf16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.C) + roff + col0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(o + j) = pk;
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) o[j] = __float2bfloat16_rn(f[j]);
+              for (int u = 0; u < 4; ++u) f[j + u] = sx::drop_keep(h, u, p16) ? f[j + u] * keep_scale : 0.f;
             }
           } else {
-            float* o = reinterpret_cast<float*>(p.C) + roff + col0;
-            if (p.accumulate) {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) atomicAdd(o + j, f[j]);
-            } else if (full) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) o[j] = f[j];
-            }
+            for (int j = 0; j < 32; ++j) f[j] = sx::drop_keep1(p.drop_seed, e0 + j, p16) ? f[j] * keep_scale : 0.f;
           }
         }
+        if (p.round_tf32 && !p.c_bf16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = sx::round_tf32(f[j]);
+        }
+        if (p.amax && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) tmax = fmaxf(tmax, f[j]);
+        }
+        coop_store(p.C, f, zoff, row0, col0, p.accumulate != 0);
       }
       sx::tc_fence_before();
       __syncwarp();
@@ -476,7 +489,7 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
   p.b_uses_z0 = a->B.stride_z0 != 0; p.b_uses_z1 = a->B.stride_z1 != 0;
   p.C = a->C; p.c_bf16 = a->c_dtype == SX_BF16; p.round_tf32 = a->round_tf32;
   p.ldc = a->ldc; p.c_sz0 = a->c_stride_z0; p.c_sz1 = a->c_stride_z1;
-  const int vec = p.c_bf16 ? 8 : 4;
+  const int vec = 4;
   p.c_vec_ok = ((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && (a->ldc % vec == 0) && (a->c_stride_z0 % vec == 0) &&
                (a->c_stride_z1 % vec == 0) &&
                (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0);

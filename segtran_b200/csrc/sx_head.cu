@@ -20,8 +20,8 @@ namespace {
 constexpr int MAXK = 8;          // max classes handled per pass
 
 // ---- forward contraction: block = 128 threads x float4 = 512 voxels, loop over channels ----
-template <int VEC>
-__global__ void __launch_bounds__(128)
+template <int VEC, int KMAX>
+__global__ void __launch_bounds__(128, (KMAX <= 4 && VEC == 4) ? 12 : 1)
 head_contract_fwd_kernel(const float* __restrict__ curr, const float* __restrict__ W, const float* __restrict__ bias,
                          int Cf, long long V, int K, float* __restrict__ L, int accumulate) {
   extern __shared__ float sW[];             // [K][Cf]
@@ -31,12 +31,12 @@ head_contract_fwd_kernel(const float* __restrict__ curr, const float* __restrict
   const long long v0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (v0 >= V) return;
   const float* src = curr + (long long)b * Cf * V + v0;
-  float acc[MAXK][VEC];
+  float acc[KMAX][VEC];
 #pragma unroll
-  for (int k = 0; k < MAXK; ++k)
+  for (int k = 0; k < KMAX; ++k)
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
   for (int c = 0; c < Cf; ++c) {
     float x[VEC];
     if constexpr (VEC == 4) {
@@ -46,7 +46,7 @@ head_contract_fwd_kernel(const float* __restrict__ curr, const float* __restrict
       x[0] = __ldg(src + (long long)c * V);
     }
 #pragma unroll
-    for (int k = 0; k < MAXK; ++k)
+    for (int k = 0; k < KMAX; ++k)
       if (k < K) {
         const float w = sW[k * Cf + c];
 #pragma unroll
@@ -54,7 +54,7 @@ head_contract_fwd_kernel(const float* __restrict__ curr, const float* __restrict
       }
   }
 #pragma unroll
-  for (int k = 0; k < MAXK; ++k)
+  for (int k = 0; k < KMAX; ++k)
     if (k < K) {
       float* dst = L + ((long long)b * K + k) * V + v0;
       const float bk = bias ? bias[k] : 0.f;
@@ -141,16 +141,17 @@ __device__ __forceinline__ void src_index(int j, float scale, int Lin, int& i0, 
   w1 = s - (float)i0;
 }
 
-__global__ void resize_axis_fwd_kernel(const float* __restrict__ x, long long outer, int Lin, int Lout, long long inner,
+template <typename I>
+__global__ void resize_axis_fwd_kernel(const float* __restrict__ x, long long outer_, int Lin, int Lout, long long inner_,
                                        float* __restrict__ y, int accumulate) {
   const float scale = (float)Lin / (float)Lout;
-  const long long total = outer * Lout * inner;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long in = idx % inner;
-    const long long t = idx / inner;
-    const int j = (int)(t % Lout);
-    const long long o = t / Lout;
+  const I inner = (I)inner_;
+  const I total = (I)(outer_ * Lout * inner_);
+  for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+    const I in = idx % inner;
+    const I t = idx / inner;
+    const int j = (int)(t % (I)Lout);
+    const I o = t / (I)Lout;
     int i0, i1;
     float w1;
     src_index(j, scale, Lin, i0, i1, w1);
@@ -161,17 +162,18 @@ __global__ void resize_axis_fwd_kernel(const float* __restrict__ x, long long ou
 }
 
 // adjoint (gather form): dx[o,i,in] = sum_j w(j->i) dy[o,j,in]
-__global__ void resize_axis_bwd_kernel(const float* __restrict__ dy, long long outer, int Lin, int Lout,
-                                       long long inner, float* __restrict__ dx) {
+template <typename I>
+__global__ void resize_axis_bwd_kernel(const float* __restrict__ dy, long long outer_, int Lin, int Lout,
+                                       long long inner_, float* __restrict__ dx) {
   const float scale = (float)Lin / (float)Lout;
   const float inv = (float)Lout / (float)Lin;
-  const long long total = outer * Lin * inner;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long in = idx % inner;
-    const long long t = idx / inner;
-    const int i = (int)(t % Lin);
-    const long long o = t / Lin;
+  const I inner = (I)inner_;
+  const I total = (I)(outer_ * Lin * inner_);
+  for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+    const I in = idx % inner;
+    const I t = idx / inner;
+    const int i = (int)(t % (I)Lin);
+    const I o = t / (I)Lin;
     int jlo = (int)floorf(((float)i - 1.f + 0.5f) * inv - 0.5f) - 1;
     int jhi = (int)ceilf(((float)i + 1.f + 0.5f) * inv - 0.5f) + 1;
     if (i == 0) jlo = 0;                       // clamped sources (s < 0) map to i = 0
@@ -246,6 +248,27 @@ __global__ void sgemm_small_kernel(const float* __restrict__ A, const float* __r
   *c = accumulate ? *c + alpha * acc : alpha * acc;
 }
 
+// same product, one WARP per output element, lanes stride over k (few outputs, long reductions)
+__global__ void sgemm_small_warp_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                        int M, int N, int K, long long sam, long long sak, long long sbk, long long sbn,
+                                        long long scm, long long scn, long long saz, long long sbz, long long scz,
+                                        float alpha, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const long long o = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= (long long)M * N) return;
+  const int m = (int)(o / N), n = (int)(o % N);
+  const long long z = blockIdx.z;
+  const float* a = A + z * saz + (long long)m * sam;
+  const float* b = B + z * sbz + (long long)n * sbn;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(a[(long long)k * sak], b[(long long)k * sbk], acc);
+  acc = sx::warp_sum(acc);
+  if (lane == 0) {
+    float* c = C + z * scz + (long long)m * scm + (long long)n * scn;
+    *c = accumulate ? *c + alpha * acc : alpha * acc;
+  }
+}
+
 }  // namespace
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -258,10 +281,13 @@ extern "C" int sx_head_contract_fwd(const float* curr, const float* W, const flo
   const bool vec4 = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(curr) & 15) == 0);
   if (vec4) {
     dim3 grid(sx_ceil_div(V, 128 * 4), B);
-    head_contract_fwd_kernel<4><<<grid, 128, smem, ST(stream)>>>(curr, W, bias, Cf, V, K, L, accumulate);
+    if (K <= 4)        // <= 42 registers: the whole grid is resident in one wave (no tail)
+      head_contract_fwd_kernel<4, 4><<<grid, 128, smem, ST(stream)>>>(curr, W, bias, Cf, V, K, L, accumulate);
+    else
+      head_contract_fwd_kernel<4, MAXK><<<grid, 128, smem, ST(stream)>>>(curr, W, bias, Cf, V, K, L, accumulate);
   } else {
     dim3 grid(sx_ceil_div(V, 128), B);
-    head_contract_fwd_kernel<1><<<grid, 128, smem, ST(stream)>>>(curr, W, bias, Cf, V, K, L, accumulate);
+    head_contract_fwd_kernel<1, MAXK><<<grid, 128, smem, ST(stream)>>>(curr, W, bias, Cf, V, K, L, accumulate);
   }
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -305,15 +331,26 @@ static int ew_grid(long long total) {
 
 extern "C" int sx_resize_axis_fwd(const float* x, int64_t outer, int32_t Lin, int32_t Lout, int64_t inner, float* y,
                                   int32_t accumulate, void* stream) {
-  resize_axis_fwd_kernel<<<ew_grid(outer * Lout * inner), 256, 0, ST(stream)>>>(x, outer, Lin, Lout, inner, y,
-                                                                               accumulate);
+  const long long big = outer * (Lin > Lout ? Lin : Lout) * inner;
+  if (big < (1ll << 31))
+    resize_axis_fwd_kernel<unsigned int><<<ew_grid(outer * Lout * inner), 256, 0, ST(stream)>>>(x, outer, Lin, Lout,
+                                                                                                 inner, y, accumulate);
+  else
+    resize_axis_fwd_kernel<long long><<<ew_grid(outer * Lout * inner), 256, 0, ST(stream)>>>(x, outer, Lin, Lout, inner,
+                                                                                              y, accumulate);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int sx_resize_axis_bwd(const float* dy, int64_t outer, int32_t Lin, int32_t Lout, int64_t inner, float* dx,
                                   void* stream) {
-  resize_axis_bwd_kernel<<<ew_grid(outer * Lin * inner), 256, 0, ST(stream)>>>(dy, outer, Lin, Lout, inner, dx);
+  const long long big = outer * (Lin > Lout ? Lin : Lout) * inner;
+  if (big < (1ll << 31))
+    resize_axis_bwd_kernel<unsigned int><<<ew_grid(outer * Lin * inner), 256, 0, ST(stream)>>>(dy, outer, Lin, Lout,
+                                                                                                inner, dx);
+  else
+    resize_axis_bwd_kernel<long long><<<ew_grid(outer * Lin * inner), 256, 0, ST(stream)>>>(dy, outer, Lin, Lout, inner,
+                                                                                             dx);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -322,6 +359,13 @@ extern "C" int sx_sgemm_small(const float* A, const float* B, float* C, int32_t 
                               int64_t sak, int64_t sbk, int64_t sbn, int64_t scm, int64_t scn, int32_t Z, int64_t saz,
                               int64_t sbz, int64_t scz, float alpha, int32_t accumulate, void* stream) {
   SX_REQUIRE(Z >= 1 && Z <= 65535, "sx_sgemm_small: batch %d out of range", Z);
+  if ((long long)M * N <= 16384 && K >= 64) {
+    dim3 grid(sx_ceil_div((long long)M * N, 8), 1, Z);
+    sgemm_small_warp_kernel<<<grid, 256, 0, ST(stream)>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, scm, scn, saz, sbz, scz,
+                                                         alpha, accumulate);
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   dim3 blk(32, 8), grid(sx_ceil_div(N, 32), sx_ceil_div(M, 8), Z);
   sgemm_small_kernel<<<grid, blk, 0, ST(stream)>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, scm, scn, saz, sbz, scz, alpha,
                                                    accumulate);

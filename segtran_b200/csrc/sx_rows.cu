@@ -161,7 +161,7 @@ __global__ void prologue_fwd_kernel(const float* __restrict__ x, long long R, in
     T* hr = h + r * C;
     for (int c = lane; c < C; c += 32) {
       float v = (row[c] - m2) * r2 * mk;
-      if (drop_p > 0.f) v = (sx::uniform_hash(seed, (unsigned long long)(r * C + c)) >= drop_p) ? v * keep_scale : 0.f;
+      if (drop_p > 0.f) v = sx::drop_keep1(seed, (unsigned long long)(r * C + c), sx::drop_p16(drop_p)) ? v * keep_scale : 0.f;
       stf<T>(hr + c, v, rnd);
     }
     if (lane == 0) {
@@ -200,7 +200,7 @@ __global__ void prologue_bwd_kernel(const float* __restrict__ dh, const float* _
       const float t = a * g[c] + b[c] + posw * per[c];
       const float yh = (t - m2) * r2;
       float d = dh[r * C + c] * mk;
-      if (drop_p > 0.f) d = (sx::uniform_hash(seed, (unsigned long long)(r * C + c)) >= drop_p) ? d * keep_scale : 0.f;
+      if (drop_p > 0.f) d = sx::drop_keep1(seed, (unsigned long long)(r * C + c), sx::drop_p16(drop_p)) ? d * keep_scale : 0.f;
       y1[c] = a; y2[c] = yh; dd[c] = d;
       s1 += d; s2 += d * yh;
     }
@@ -263,7 +263,7 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ S, long long R, int
     T* pr = P + r * ldp;
     for (int c = lane; c < L; c += 32) {
       float v = row[c] * inv;
-      if (drop_p > 0.f) v = (sx::uniform_hash(seed, (unsigned long long)(r * ldp + c)) >= drop_p) ? v * keep_scale : 0.f;
+      if (drop_p > 0.f) v = sx::drop_keep1(seed, (unsigned long long)(r * ldp + c), sx::drop_p16(drop_p)) ? v * keep_scale : 0.f;
       stf<T>(pr + c, v, rnd);
     }
     if (lane == 0 && lse) lse[r] = m + __logf(s);
@@ -293,7 +293,7 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ dP, long long ldd, 
       const float pv = __expf(v - l);
       float gv = dP[r * ldd + c];
       if (drop_p > 0.f)
-        gv = (sx::uniform_hash(seed, (unsigned long long)(r * ldp_fwd + c)) >= drop_p) ? gv * keep_scale : 0.f;
+        gv = sx::drop_keep1(seed, (unsigned long long)(r * ldp_fwd + c), sx::drop_p16(drop_p)) ? gv * keep_scale : 0.f;
       prow[c] = pv; grow[c] = gv;
       dot += pv * gv;
     }
@@ -389,7 +389,7 @@ __global__ void ln_softaggr_fwd_kernel(const float* __restrict__ Y, int B, int M
       for (int c = lane; c < F; c += 32) {
         float v = yr[c];
         if (drop_p > 0.f)
-          v = (sx::uniform_hash(seed, (unsigned long long)(ro * F + c)) >= drop_p) ? v * keep_scale : 0.f;
+          v = sx::drop_keep1(seed, (unsigned long long)(ro * F + c), sx::drop_p16(drop_p)) ? v * keep_scale : 0.f;
         row[c] = v;
       }
       __syncwarp();
@@ -453,7 +453,7 @@ __global__ void ln_softaggr_bwd_kernel(const float* __restrict__ dout, const flo
       for (int c = lane; c < F; c += 32) {
         float v = Y[ro * F + c];
         if (drop_p > 0.f)
-          v = (sx::uniform_hash(seed, (unsigned long long)(ro * F + c)) >= drop_p) ? v * keep_scale : 0.f;
+          v = sx::drop_keep1(seed, (unsigned long long)(ro * F + c), sx::drop_p16(drop_p)) ? v * keep_scale : 0.f;
         dot += go[c] * ((v - mean) * rstd * g[c] + b[c]);
       }
       dwm[m] = sx::warp_sum(dot);
@@ -470,7 +470,7 @@ __global__ void ln_softaggr_bwd_kernel(const float* __restrict__ dout, const flo
       for (int c = lane; c < F; c += 32) {
         float v = Y[ro * F + c];
         if (drop_p > 0.f)
-          v = (sx::uniform_hash(seed, (unsigned long long)(ro * F + c)) >= drop_p) ? v * keep_scale : 0.f;
+          v = sx::drop_keep1(seed, (unsigned long long)(ro * F + c), sx::drop_p16(drop_p)) ? v * keep_scale : 0.f;
         const float a = (v - mean) * rstd;
         const float yn = a * g[c] + b[c];
         const float dyn = w[m] * go[c] + dscore * ws[c];
@@ -485,7 +485,7 @@ __global__ void ln_softaggr_bwd_kernel(const float* __restrict__ dout, const flo
       for (int c = lane; c < F; c += 32) {
         float d = rstd * (dd[c] - s1 - yh[c] * s2);
         if (drop_p > 0.f)
-          d = (sx::uniform_hash(seed, (unsigned long long)(ro * F + c)) >= drop_p) ? d * keep_scale : 0.f;
+          d = sx::drop_keep1(seed, (unsigned long long)(ro * F + c), sx::drop_p16(drop_p)) ? d * keep_scale : 0.f;
         stf<T>(dY + ro * F + c, d, rnd);
       }
       __syncwarp();
@@ -500,6 +500,8 @@ __global__ void ln_softaggr_bwd_kernel(const float* __restrict__ dout, const flo
   if (lane == 0) atomicAdd(dbs, dbs_acc);     // identical in all lanes of the warp
 }
 
+#include "sx_rows_fast.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // elementwise helpers
 // ------------------------------------------------------------------------------------------------
@@ -510,8 +512,21 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ dG, const TH* __restri
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float d = dG[i];
-    if (drop_p > 0.f) d = (sx::uniform_hash(seed, (unsigned long long)i) >= drop_p) ? d * keep_scale : 0.f;
+    if (drop_p > 0.f) d = sx::drop_keep1(seed, (unsigned long long)i, sx::drop_p16(drop_p)) ? d * keep_scale : 0.f;
     stf<TO>(dH + i, d * sx::gelu_erf_grad(ldf<TH>(H + i)), rnd);
+  }
+}
+
+// fp32 float4 version (n % 4 == 0, 16-byte aligned)
+__global__ void gelu_bwd_f4_kernel(const float4* __restrict__ dG, const float4* __restrict__ H, long long n4, float drop_p,
+                                   unsigned long long seed, float4* __restrict__ dH, int rnd) {
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 d = dG[i];
+    if (drop_p > 0.f) d = drop4(d, drop_p, keep_scale, seed, (unsigned long long)(i * 4));
+    const float4 h = H[i];
+    d.x *= sx::gelu_erf_grad(h.x); d.y *= sx::gelu_erf_grad(h.y); d.z *= sx::gelu_erf_grad(h.z); d.w *= sx::gelu_erf_grad(h.w);
+    dH[i] = rnd4(d, rnd);
   }
 }
 
@@ -536,6 +551,28 @@ __global__ void colsum_kernel(const T* __restrict__ X, long long R, int C, long 
     float t = 0.f;
     for (int y = 0; y < 8; ++y) t += s[y][threadIdx.x];
     atomicAdd(&out[c], t);
+  }
+}
+
+// out[z0*C + c] += sum_{z1,r} X[z1*sz1 + z0*sz0 + r*ld + c]   (per-mode bias gradients in one launch).  blockDim (32, 8)
+__global__ void colsum_batched_kernel(const float* __restrict__ X, int Z1, long long sz1, long long sz0, long long R,
+                                      int C, long long ld, float* __restrict__ out) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int z0 = blockIdx.z;
+  float acc = 0.f;
+  if (c < C)
+    for (int z1 = 0; z1 < Z1; ++z1) {
+      const float* base = X + z1 * sz1 + z0 * sz0;
+      for (long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.y * blockDim.y)
+        acc += base[r * ld + c];
+    }
+  __shared__ float s[8][33];
+  s[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+    for (int y = 0; y < 8; ++y) t += s[y][threadIdx.x];
+    atomicAdd(&out[(long long)z0 * C + c], t);
   }
 }
 
@@ -685,7 +722,32 @@ extern "C" int sx_prologue_fwd(const float* x, int64_t B, int32_t N, int32_t C, 
 extern "C" int sx_prologue_bwd(const float* dh, const float* x, int64_t B, int32_t N, int32_t C, const float* g,
                                const float* b, const float* pe, int32_t C0, int64_t pe_bstride, float posw,
                                const float* mask, float drop_p, uint64_t seed, const float* stats, float* dx, float* dg,
-                               float* db, float* dpe, void* stream) {
+                               float* db, float* dpe, float* dt_scratch, void* stream) {
+  if (dt_scratch && C % 4 == 0 && C0 % 4 == 0 && pe_bstride % 4 == 0 && nv_for(C) && al16(dh) && al16(x) && al16(dx) &&
+      al16(pe) && al16(g) && al16(b) && al16(dt_scratch) && (!dpe || al16(dpe))) {
+    const long long R = (long long)B * N;
+    const int grid = grid_for_rows(R, FAST_WARPS, sms_cached() * 2);
+#define SX_LAUNCH(NV_)                                                                                                \
+  prologue_bwd_rows_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(dh, x, R, N, C, g, b, pe, C0, pe_bstride, posw, \
+                                                                        mask, drop_p, seed, stats, dx, dt_scratch)
+    switch (nv_for(C)) { case 2: SX_LAUNCH(2); break; case 4: SX_LAUNCH(4); break; case 8: SX_LAUNCH(8); break;
+                         default: SX_LAUNCH(16); }
+#undef SX_LAUNCH
+    SX_CHECK_CUDA(cudaGetLastError());
+    int gy = (int)((R + 8 * 64 - 1) / (8 * 64));
+    const int cap = sx_ceil_div(sms_cached() * 8, sx_ceil_div(C, 128));
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    dim3 grid2(sx_ceil_div(C, 128), gy), blk(32, 8);
+    ln_param_grad_cols_fast<<<grid2, blk, 0, ST(stream)>>>(dt_scratch, x, R, C, stats, 4, dg, db);
+    SX_CHECK_CUDA(cudaGetLastError());
+    if (dpe) {
+      pos_grad_from_dt_fast<<<grid_for_rows((long long)N * (C / 4), 256, sms_cached()), 256, 0, ST(stream)>>>(
+          dt_scratch, (int)B, N, C, C0, pe_bstride, posw, dpe);
+      SX_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
   const size_t smem = (size_t)(2 + 3 * ROW_WARPS) * C * 4;
   SX_REQUIRE(smem <= 220 * 1024, "sx_prologue_bwd: C=%d too large", C);
   if (set_smem(prologue_bwd_kernel, smem)) return -2;
@@ -705,6 +767,17 @@ static int softmax_warps(int L, int per_row_floats) {
 extern "C" int sx_softmax_fwd(const float* S, int64_t R, int32_t L, int64_t lds, const float* amax, float clip,
                               float drop_p, uint64_t seed, void* P, int32_t p_dtype, int64_t ldp, int32_t round_tf32,
                               float* lse, float* diag, void* stream) {
+  if (p_dtype == SX_F32 && L % 4 == 0 && lds % 4 == 0 && ldp % 4 == 0 && al16(S) && al16(P) && nv_for(L)) {
+    const int grid = grid_for_rows(R, FAST_WARPS, sms_cached() * 2);
+#define SX_LAUNCH(NV_)                                                                                          \
+  softmax_fwd_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(S, R, L, lds, amax, clip, drop_p, seed, (float*)P, \
+                                                                  ldp, lse, round_tf32, diag)
+    switch (nv_for(L)) { case 2: SX_LAUNCH(2); break; case 4: SX_LAUNCH(4); break; case 8: SX_LAUNCH(8); break;
+                         default: SX_LAUNCH(16); }
+#undef SX_LAUNCH
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int w = softmax_warps(L, 1);
   SX_REQUIRE(w >= 1, "sx_softmax_fwd: row length %d too large", L);
   const size_t smem = (size_t)w * L * 4;
@@ -725,6 +798,18 @@ extern "C" int sx_softmax_fwd(const float* S, int64_t R, int32_t L, int64_t lds,
 extern "C" int sx_softmax_bwd(const float* dP, int64_t ldd, const float* S, int64_t lds, const float* lse, int64_t R,
                               int32_t L, const float* amax, float clip, float drop_p, uint64_t seed, int64_t ldp_fwd,
                               void* dS, int32_t ds_dtype, int64_t ldo, int32_t round_tf32, void* stream) {
+  if (ds_dtype == SX_F32 && L % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ldo % 4 == 0 && al16(S) && al16(dP) &&
+      al16(dS) && nv_for(L)) {
+    const int grid = grid_for_rows(R, FAST_WARPS, sms_cached() * 2);
+#define SX_LAUNCH(NV_)                                                                                             \
+  softmax_bwd_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(dP, ldd, S, lds, lse, R, L, amax, clip, drop_p, seed, \
+                                                                  ldp_fwd, (float*)dS, ldo, round_tf32)
+    switch (nv_for(L)) { case 2: SX_LAUNCH(2); break; case 4: SX_LAUNCH(4); break; case 8: SX_LAUNCH(8); break;
+                         default: SX_LAUNCH(16); }
+#undef SX_LAUNCH
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int w = softmax_warps(L, 2);
   SX_REQUIRE(w >= 1, "sx_softmax_bwd: row length %d too large", L);
   const size_t smem = (size_t)w * 2 * L * 4;
@@ -762,6 +847,23 @@ extern "C" int sx_layernorm_fwd(const float* x, int64_t R, int32_t C, const floa
 extern "C" int sx_layernorm_bwd(const float* dy, const float* x, int64_t R, int32_t C, const float* g,
                                 const float* stats, void* dx, int32_t dx_dtype, int32_t round_tf32, float* dg, float* db,
                                 void* stream) {
+  if (dx_dtype == SX_F32 && C % 4 == 0 && nv_for(C) && al16(dy) && al16(x) && al16(dx) && al16(g)) {
+    const int grid = grid_for_rows(R, FAST_WARPS, sms_cached() * 2);
+#define SX_LAUNCH(NV_)                                                                                         \
+  layernorm_bwd_rows_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(dy, x, R, C, g, stats, (float*)dx, round_tf32)
+    switch (nv_for(C)) { case 2: SX_LAUNCH(2); break; case 4: SX_LAUNCH(4); break; case 8: SX_LAUNCH(8); break;
+                         default: SX_LAUNCH(16); }
+#undef SX_LAUNCH
+    SX_CHECK_CUDA(cudaGetLastError());
+    int gy = (int)((R + 8 * 64 - 1) / (8 * 64));
+    const int cap = sx_ceil_div(sms_cached() * 8, sx_ceil_div(C, 128));
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    dim3 grid2(sx_ceil_div(C, 128), gy), blk(32, 8);
+    ln_param_grad_cols_fast<<<grid2, blk, 0, ST(stream)>>>(dy, x, R, C, stats, 2, dg, db);
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t smem = (size_t)(2 + 2 * ROW_WARPS) * C * 4;
   SX_REQUIRE(smem <= 220 * 1024, "sx_layernorm_bwd: C=%d too large", C);
   const int grid = grid_for_rows(R, ROW_WARPS * 4, sms_cached());
@@ -782,6 +884,17 @@ extern "C" int sx_ln_softaggr_fwd(const float* Y, int32_t B, int32_t M, int32_t 
                                   const float* b, const float* ws, const float* bs, float drop_p, uint64_t seed,
                                   float* out, float* stats, float* wts, void* stream) {
   SX_REQUIRE(M >= 1 && M <= MAX_MODES, "sx_ln_softaggr_fwd: num_modes %d not in 1..%d", M, MAX_MODES);
+  if (F % 4 == 0 && nv_for(F) && al16(Y) && al16(out) && al16(g) && al16(b) && al16(ws)) {
+    const int grid = grid_for_rows((long long)B * N, FAST_WARPS, sms_cached() * 2);
+#define SX_LAUNCH(NV_)                                                                                          \
+  ln_softaggr_fwd_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(Y, B, M, N, F, g, b, ws, bs, drop_p, seed, out, \
+                                                                      stats, wts)
+    switch (nv_for(F)) { case 2: SX_LAUNCH(2); break; case 4: SX_LAUNCH(4); break; case 8: SX_LAUNCH(8); break;
+                         default: SX_LAUNCH(16); }
+#undef SX_LAUNCH
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   int warps = (int)((200 * 1024) / ((size_t)M * F * 4));
   if (warps > ROW_WARPS) warps = ROW_WARPS;
   SX_REQUIRE(warps == ROW_WARPS, "sx_ln_softaggr_fwd: M*F=%d too large for 8 rows in shared memory", M * F);
@@ -796,8 +909,30 @@ extern "C" int sx_ln_softaggr_fwd(const float* Y, int32_t B, int32_t M, int32_t 
 extern "C" int sx_ln_softaggr_bwd(const float* dout, const float* Y, int32_t B, int32_t M, int32_t N, int32_t F,
                                   const float* g, const float* b, const float* ws, float drop_p, uint64_t seed,
                                   const float* stats, const float* wts, void* dY, int32_t dy_dtype, int32_t round_tf32,
-                                  float* dg, float* db, float* dws, float* dbs, void* stream) {
+                                  float* dg, float* db, float* dws, float* dbs, float* dscore_scratch, void* stream) {
   SX_REQUIRE(M >= 1 && M <= MAX_MODES, "sx_ln_softaggr_bwd: num_modes %d not in 1..%d", M, MAX_MODES);
+  if (dy_dtype == SX_F32 && dscore_scratch && F % 4 == 0 && nv_for(F) && al16(Y) && al16(dout) && al16(dY) && al16(g) &&
+      al16(b) && al16(ws)) {
+    const int grid = grid_for_rows((long long)B * N, FAST_WARPS, sms_cached() * 2);
+#define SX_LAUNCH(NV_)                                                                                              \
+  ln_softaggr_bwd_rows_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(dout, Y, B, M, N, F, g, b, ws, drop_p, seed, \
+                                                                           stats, wts, (float*)dY, dscore_scratch, dbs, \
+                                                                           round_tf32)
+    switch (nv_for(F)) { case 2: SX_LAUNCH(2); break; case 4: SX_LAUNCH(4); break; case 8: SX_LAUNCH(8); break;
+                         default: SX_LAUNCH(16); }
+#undef SX_LAUNCH
+    SX_CHECK_CUDA(cudaGetLastError());
+    const long long R = (long long)B * M * N;
+    int gy = (int)((R + 8 * 64 - 1) / (8 * 64));
+    const int cap = sx_ceil_div(sms_cached() * 8, sx_ceil_div(F, 128));
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    dim3 grid2(sx_ceil_div(F, 128), gy), blk(32, 8);
+    ln_softaggr_bwd_cols_fast<<<grid2, blk, 0, ST(stream)>>>(dout, Y, B, M, N, F, g, b, ws, drop_p, seed, stats, wts,
+                                                             dscore_scratch, dg, db, dws);
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t smem = (size_t)(3 + 2 * ROW_WARPS) * F * 4;
   SX_REQUIRE(smem <= 220 * 1024, "sx_ln_softaggr_bwd: F=%d too large", F);
   const int grid = grid_for_rows((long long)B * N, ROW_WARPS * 4, sms_cached());
@@ -818,7 +953,10 @@ extern "C" int sx_gelu_bwd(const float* dG, const void* H, int32_t h_dtype, int6
                            void* dH, int32_t dh_dtype, int32_t round_tf32, void* stream) {
   const int grid = grid_for_rows(n, 256 * 8, sms_cached());
   SX_REQUIRE(h_dtype == dh_dtype, "sx_gelu_bwd: H and dH dtypes must match");
-  if (h_dtype == SX_F32)
+  if (h_dtype == SX_F32 && n % 4 == 0 && al16(dG) && al16(H) && al16(dH))
+    gelu_bwd_f4_kernel<<<grid_for_rows(n / 4, 256 * 4, sms_cached()), 256, 0, ST(stream)>>>(
+        (const float4*)dG, (const float4*)H, n / 4, drop_p, seed, (float4*)dH, round_tf32);
+  else if (h_dtype == SX_F32)
     gelu_bwd_kernel<float, float><<<grid, 256, 0, ST(stream)>>>(dG, (const float*)H, n, drop_p, seed, (float*)dH,
                                                                  round_tf32);
   else
@@ -879,6 +1017,18 @@ extern "C" int sx_scale(const float* x, int64_t n, const float* alpha_dev, float
 extern "C" int sx_rowsum(const float* X, int64_t R, int64_t C, int64_t ld, int32_t out_mod, float* out, void* stream) {
   SX_REQUIRE(R >= 1 && R <= 2147483647ll && out_mod >= 1, "sx_rowsum: bad shape");
   rowsum_kernel<<<(unsigned)R, 512, 0, ST(stream)>>>(X, C, ld, out_mod, out);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_colsum_batched(const float* X, int32_t Z1, int64_t stride_z1, int32_t Z0, int64_t stride_z0, int64_t R,
+                                 int32_t C, int64_t ld, float* out, void* stream) {
+  SX_REQUIRE(Z0 >= 1 && Z0 <= 65535 && Z1 >= 1, "sx_colsum_batched: bad batch dims");
+  int gy = (int)((R + 255) / 256);
+  if (gy > 32) gy = 32;
+  if (gy < 1) gy = 1;
+  dim3 grid(sx_ceil_div(C, 32), gy, Z0), blk(32, 8);
+  colsum_batched_kernel<<<grid, blk, 0, ST(stream)>>>(X, Z1, stride_z1, stride_z0, R, C, ld, out);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

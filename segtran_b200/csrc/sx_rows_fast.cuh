@@ -1,0 +1,540 @@
+// Register-resident fast paths of the row kernels (fp32 I/O, row length a multiple of 4, <= 128*NV floats).
+// A row lives in NV float4 registers per lane (lane l holds columns 4l+128i .. +3), so there is no shared-memory
+// staging, occupancy is register-limited only (32+ warps/SM) and every global access is a 16-byte vector access.
+// Parameter gradients that are column sums over all rows are produced by separate column-parallel reductions
+// instead of shared-memory atomics.  Included by sx_rows.cu inside its anonymous namespace.
+#pragma once
+
+template <int NV>
+__device__ __forceinline__ void row_load(float4 (&v)[NV], const float* __restrict__ p, int C, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = 4 * lane + 128 * i;
+    v[i] = (c < C) ? *reinterpret_cast<const float4*>(p + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void row_store(const float4 (&v)[NV], float* __restrict__ p, int C, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = 4 * lane + 128 * i;
+    if (c < C) *reinterpret_cast<float4*>(p + c) = v[i];
+  }
+}
+template <int NV>
+__device__ __forceinline__ void row_mean_rstd(const float4 (&v)[NV], int C, int lane, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);     // out-of-range entries are zero
+  mean = sx::warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (4 * lane + 128 * i < C) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  rstd = rsqrtf(sx::warp_sum(q) / C + LN_EPS);
+}
+// idx must be a multiple of 4 (start of a float4 group)
+__device__ __forceinline__ float4 drop4(float4 v, float p, float scale, unsigned long long seed, unsigned long long idx) {
+  const uint2 h = sx::drop_hash(seed, idx >> 2);
+  const uint32_t p16 = sx::drop_p16(p);
+  v.x = sx::drop_keep(h, 0, p16) ? v.x * scale : 0.f;
+  v.y = sx::drop_keep(h, 1, p16) ? v.y * scale : 0.f;
+  v.z = sx::drop_keep(h, 2, p16) ? v.z * scale : 0.f;
+  v.w = sx::drop_keep(h, 3, p16) ? v.w * scale : 0.f;
+  return v;
+}
+__device__ __forceinline__ float4 rnd4(float4 v, int rnd) {
+  if (rnd) { v.x = sx::round_tf32(v.x); v.y = sx::round_tf32(v.y); v.z = sx::round_tf32(v.z); v.w = sx::round_tf32(v.w); }
+  return v;
+}
+__device__ __forceinline__ float4 ld4(const float* __restrict__ p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+constexpr int FAST_WARPS = 8;
+
+// ------------------------------------------------------------------------------------------------
+// LN + soft aggregate, forward.  Pass 1 per mode: stats + score; pass 2 re-reads the (L2-resident) rows.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+ln_softaggr_fwd_fast(const float* __restrict__ Y, int B, int M, int N, int F, const float* __restrict__ g,
+                     const float* __restrict__ b, const float* __restrict__ ws, const float* __restrict__ bs,
+                     float drop_p, unsigned long long seed, float* __restrict__ out, float* __restrict__ stats,
+                     float* __restrict__ wts) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const long long T_ = (long long)B * N;
+  for (long long t = (long long)blockIdx.x * FAST_WARPS + warp; t < T_; t += (long long)gridDim.x * FAST_WARPS) {
+    const long long bi = t / N, ni = t % N;
+    float sc[MAX_MODES], mu[MAX_MODES], rs[MAX_MODES];
+#pragma unroll
+    for (int m = 0; m < MAX_MODES; ++m)
+      if (m < M) {
+        const long long ro = (bi * M + m) * N + ni;
+        float4 v[NV];
+        row_load<NV>(v, Y + ro * F, F, lane);
+        if (drop_p > 0.f) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            if (4 * lane + 128 * i < F) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + 4 * lane + 128 * i));
+        }
+        float mean, rstd;
+        row_mean_rstd<NV>(v, F, lane, mean, rstd);
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = 4 * lane + 128 * i;
+          if (c < F) {
+            const float4 gg = ld4(g + c), bb = ld4(b + c), ww = ld4(ws + c);
+            dot += ((v[i].x - mean) * rstd * gg.x + bb.x) * ww.x + ((v[i].y - mean) * rstd * gg.y + bb.y) * ww.y +
+                   ((v[i].z - mean) * rstd * gg.z + bb.z) * ww.z + ((v[i].w - mean) * rstd * gg.w + bb.w) * ww.w;
+          }
+        }
+        sc[m] = sx::warp_sum(dot) + bs[0];
+        mu[m] = mean; rs[m] = rstd;
+        if (lane == 0) { stats[ro * 2] = mean; stats[ro * 2 + 1] = rstd; }
+      }
+    float mx = -3.0e38f;
+#pragma unroll
+    for (int m = 0; m < MAX_MODES; ++m) if (m < M) mx = fmaxf(mx, sc[m]);
+    float den = 0.f;
+#pragma unroll
+    for (int m = 0; m < MAX_MODES; ++m) if (m < M) { sc[m] = __expf(sc[m] - mx); den += sc[m]; }
+#pragma unroll
+    for (int m = 0; m < MAX_MODES; ++m) if (m < M) sc[m] /= den;
+    if (lane == 0)
+      for (int m = 0; m < M; ++m) wts[(bi * M + m) * N + ni] = sc[m];
+    float4 o[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < MAX_MODES; ++m)
+      if (m < M) {
+        const long long ro = (bi * M + m) * N + ni;
+        float4 v[NV];
+        row_load<NV>(v, Y + ro * F, F, lane);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = 4 * lane + 128 * i;
+          if (c < F) {
+            if (drop_p > 0.f) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
+            const float4 gg = ld4(g + c), bb = ld4(b + c);
+            const float w = sc[m], mean = mu[m], rstd = rs[m];
+            o[i].x += w * ((v[i].x - mean) * rstd * gg.x + bb.x);
+            o[i].y += w * ((v[i].y - mean) * rstd * gg.y + bb.y);
+            o[i].z += w * ((v[i].z - mean) * rstd * gg.z + bb.z);
+            o[i].w += w * ((v[i].w - mean) * rstd * gg.w + bb.w);
+          }
+        }
+      }
+    row_store<NV>(o, out + t * F, F, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LN + soft aggregate, backward, row part: dY and the per-(mode,token) score gradient (kept for the column pass)
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+ln_softaggr_bwd_rows_fast(const float* __restrict__ dout, const float* __restrict__ Y, int B, int M, int N, int F,
+                          const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ ws,
+                          float drop_p, unsigned long long seed, const float* __restrict__ stats,
+                          const float* __restrict__ wts, float* __restrict__ dY, float* __restrict__ dscore_out,
+                          float* __restrict__ dbs, int rnd) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const long long T_ = (long long)B * N;
+  float dbs_acc = 0.f;
+  for (long long t = (long long)blockIdx.x * FAST_WARPS + warp; t < T_; t += (long long)gridDim.x * FAST_WARPS) {
+    const long long bi = t / N, ni = t % N;
+    float4 go[NV];
+    row_load<NV>(go, dout + t * F, F, lane);
+    float dwm[MAX_MODES], w[MAX_MODES];
+#pragma unroll
+    for (int m = 0; m < MAX_MODES; ++m)
+      if (m < M) {
+        const long long ro = (bi * M + m) * N + ni;
+        const float mean = stats[ro * 2], rstd = stats[ro * 2 + 1];
+        float4 v[NV];
+        row_load<NV>(v, Y + ro * F, F, lane);
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = 4 * lane + 128 * i;
+          if (c < F) {
+            if (drop_p > 0.f) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
+            const float4 gg = ld4(g + c), bb = ld4(b + c);
+            dot += go[i].x * ((v[i].x - mean) * rstd * gg.x + bb.x) + go[i].y * ((v[i].y - mean) * rstd * gg.y + bb.y) +
+                   go[i].z * ((v[i].z - mean) * rstd * gg.z + bb.z) + go[i].w * ((v[i].w - mean) * rstd * gg.w + bb.w);
+          }
+        }
+        dwm[m] = sx::warp_sum(dot);
+        w[m] = wts[(bi * M + m) * N + ni];
+      }
+    float wd = 0.f;
+#pragma unroll
+    for (int m = 0; m < MAX_MODES; ++m) if (m < M) wd += w[m] * dwm[m];
+#pragma unroll
+    for (int m = 0; m < MAX_MODES; ++m)
+      if (m < M) {
+        const float dscore = w[m] * (dwm[m] - wd);
+        dbs_acc += dscore;
+        const long long ro = (bi * M + m) * N + ni;
+        if (lane == 0) dscore_out[ro] = dscore;
+        const float mean = stats[ro * 2], rstd = stats[ro * 2 + 1];
+        float4 v[NV], d[NV];
+        row_load<NV>(v, Y + ro * F, F, lane);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = 4 * lane + 128 * i;
+          d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < F) {
+            if (drop_p > 0.f) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
+            const float4 gg = ld4(g + c), ww = ld4(ws + c);
+            v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
+            v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
+            d[i].x = (w[m] * go[i].x + dscore * ww.x) * gg.x; d[i].y = (w[m] * go[i].y + dscore * ww.y) * gg.y;
+            d[i].z = (w[m] * go[i].z + dscore * ww.z) * gg.z; d[i].w = (w[m] * go[i].w + dscore * ww.w) * gg.w;
+            s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+            s2 += (d[i].x * v[i].x + d[i].y * v[i].y) + (d[i].z * v[i].z + d[i].w * v[i].w);
+          }
+        }
+        s1 = sx::warp_sum(s1) / F; s2 = sx::warp_sum(s2) / F;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = 4 * lane + 128 * i;
+          if (c < F) {
+            float4 r;
+            r.x = rstd * (d[i].x - s1 - v[i].x * s2); r.y = rstd * (d[i].y - s1 - v[i].y * s2);
+            r.z = rstd * (d[i].z - s1 - v[i].z * s2); r.w = rstd * (d[i].w - s1 - v[i].w * s2);
+            if (drop_p > 0.f) r = drop4(r, drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
+            *reinterpret_cast<float4*>(dY + ro * F + c) = rnd4(r, rnd);
+          }
+        }
+      }
+  }
+  if (lane == 0 && dbs_acc != 0.f) atomicAdd(dbs, dbs_acc);
+}
+
+// column part: dg[c] += sum_r dyn a ; db[c] += sum_r dyn ; dws[c] += sum_r dscore yn   (r over all (b,m,n) rows)
+// block (32 lanes x 8 row-slots); lane owns 4 consecutive columns.
+__global__ void __launch_bounds__(256)
+ln_softaggr_bwd_cols_fast(const float* __restrict__ dout, const float* __restrict__ Y, int B, int M, int N, int F,
+                          const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ ws,
+                          float drop_p, unsigned long long seed, const float* __restrict__ stats,
+                          const float* __restrict__ wts, const float* __restrict__ dscore_in, float* __restrict__ dg,
+                          float* __restrict__ db, float* __restrict__ dws) {
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, aw = ag;
+  const long long R = (long long)B * M * N;
+  if (c < F) {
+    const float4 gg = ld4(g + c), bb = ld4(b + c), ww = ld4(ws + c);
+    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < R; r += (long long)gridDim.y * 8) {
+      const long long bm = r / N, ni = r % N, bi = bm / M;
+      const float mean = stats[r * 2], rstd = stats[r * 2 + 1], w = wts[r], ds = dscore_in[r];
+      float4 v = ld4(Y + r * F + c);
+      if (drop_p > 0.f) v = drop4(v, drop_p, keep_scale, seed, (unsigned long long)(r * F + c));
+      const float4 go = ld4(dout + (bi * N + ni) * F + c);
+      const float a0 = (v.x - mean) * rstd, a1 = (v.y - mean) * rstd, a2 = (v.z - mean) * rstd, a3 = (v.w - mean) * rstd;
+      const float d0 = w * go.x + ds * ww.x, d1 = w * go.y + ds * ww.y, d2 = w * go.z + ds * ww.z, d3 = w * go.w + ds * ww.w;
+      ag.x += d0 * a0; ag.y += d1 * a1; ag.z += d2 * a2; ag.w += d3 * a3;
+      ab.x += d0; ab.y += d1; ab.z += d2; ab.w += d3;
+      aw.x += ds * (a0 * gg.x + bb.x); aw.y += ds * (a1 * gg.y + bb.y);
+      aw.z += ds * (a2 * gg.z + bb.z); aw.w += ds * (a3 * gg.w + bb.w);
+    }
+  }
+  __shared__ float4 s[3][8][32];
+  s[0][threadIdx.y][threadIdx.x] = ag; s[1][threadIdx.y][threadIdx.x] = ab; s[2][threadIdx.y][threadIdx.x] = aw;
+  __syncthreads();
+  if (threadIdx.y < 3 && c < F) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = 0; y < 8; ++y) {
+      const float4 u = s[threadIdx.y][y][threadIdx.x];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    float* dst = threadIdx.y == 0 ? dg : (threadIdx.y == 1 ? db : dws);
+    atomicAdd(dst + c, t.x); atomicAdd(dst + c + 1, t.y); atomicAdd(dst + c + 2, t.z); atomicAdd(dst + c + 3, t.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax forward / backward with the row in registers (L <= 128*NV)
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+softmax_fwd_fast(const float* __restrict__ S, long long R, int L, long long lds, const float* __restrict__ amax,
+                 float clip, float drop_p, unsigned long long seed, float* __restrict__ P, long long ldp,
+                 float* __restrict__ lse, int rnd, float* __restrict__ diag) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool do_clip = amax && (*amax > clip);
+  if (diag && amax && blockIdx.x == 0 && threadIdx.x == 0) {
+    diag[0] = fmaxf(diag[0], *amax);
+    if (do_clip) diag[1] += 1.f;
+  }
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (long long r = (long long)blockIdx.x * FAST_WARPS + warp; r < R; r += (long long)gridDim.x * FAST_WARPS) {
+    float4 v[NV];
+    row_load<NV>(v, S + r * lds, L, lane);
+    float m = -3.0e38f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (4 * lane + 128 * i < L) {
+        if (do_clip) {
+          v[i].x = fminf(fmaxf(v[i].x, -clip), clip); v[i].y = fminf(fmaxf(v[i].y, -clip), clip);
+          v[i].z = fminf(fmaxf(v[i].z, -clip), clip); v[i].w = fminf(fmaxf(v[i].w, -clip), clip);
+        }
+        m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+      }
+    m = sx::warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (4 * lane + 128 * i < L) {
+        v[i].x = __expf(v[i].x - m); v[i].y = __expf(v[i].y - m); v[i].z = __expf(v[i].z - m); v[i].w = __expf(v[i].w - m);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    s = sx::warp_sum(s);
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * lane + 128 * i;
+      if (c < L) {
+        float4 p = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+        if (drop_p > 0.f) p = drop4(p, drop_p, keep_scale, seed, (unsigned long long)(r * ldp + c));
+        *reinterpret_cast<float4*>(P + r * ldp + c) = rnd4(p, rnd);
+      }
+    }
+    if (lane == 0 && lse) lse[r] = m + __logf(s);
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+softmax_bwd_fast(const float* __restrict__ dP, long long ldd, const float* __restrict__ S, long long lds,
+                 const float* __restrict__ lse, long long R, int L, const float* __restrict__ amax, float clip,
+                 float drop_p, unsigned long long seed, long long ldp_fwd, float* __restrict__ dS, long long ldo,
+                 int rnd) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool do_clip = amax && (*amax > clip);
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (long long r = (long long)blockIdx.x * FAST_WARPS + warp; r < R; r += (long long)gridDim.x * FAST_WARPS) {
+    const float l = lse[r];
+    float4 p[NV], gv[NV];
+    row_load<NV>(p, S + r * lds, L, lane);
+    row_load<NV>(gv, dP + r * ldd, L, lane);
+    float dot = 0.f;
+    unsigned inside = 0;                        // bit i*4+j: element was inside the clamp range
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * lane + 128 * i;
+      if (c < L) {
+        float x[4] = {p[i].x, p[i].y, p[i].z, p[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          bool in = true;
+          if (do_clip) { in = (x[j] >= -clip && x[j] <= clip); x[j] = fminf(fmaxf(x[j], -clip), clip); }
+          if (in && NV <= 8) inside |= 1u << (i * 4 + j);
+          x[j] = __expf(x[j] - l);
+        }
+        p[i] = make_float4(x[0], x[1], x[2], x[3]);
+        if (drop_p > 0.f) gv[i] = drop4(gv[i], drop_p, keep_scale, seed, (unsigned long long)(r * ldp_fwd + c));
+        dot += (p[i].x * gv[i].x + p[i].y * gv[i].y) + (p[i].z * gv[i].z + p[i].w * gv[i].w);
+      } else {
+        p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    dot = sx::warp_sum(dot);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * lane + 128 * i;
+      if (c < L) {
+        float4 d = make_float4(p[i].x * (gv[i].x - dot), p[i].y * (gv[i].y - dot), p[i].z * (gv[i].z - dot),
+                               p[i].w * (gv[i].w - dot));
+        if (do_clip) {
+          if (NV <= 8) {
+            if (!(inside >> (i * 4 + 0) & 1u)) d.x = 0.f;
+            if (!(inside >> (i * 4 + 1) & 1u)) d.y = 0.f;
+            if (!(inside >> (i * 4 + 2) & 1u)) d.z = 0.f;
+            if (!(inside >> (i * 4 + 3) & 1u)) d.w = 0.f;
+          } else {
+            const float4 raw = ld4(S + r * lds + c);
+            if (raw.x < -clip || raw.x > clip) d.x = 0.f;
+            if (raw.y < -clip || raw.y > clip) d.y = 0.f;
+            if (raw.z < -clip || raw.z > clip) d.z = 0.f;
+            if (raw.w < -clip || raw.w > clip) d.w = 0.f;
+          }
+        }
+        *reinterpret_cast<float4*>(dS + r * ldo + c) = rnd4(d, rnd);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prologue backward: row part (dx, and dt = gradient at the inner LayerNorm's input, kept for the column pass)
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+prologue_bwd_rows_fast(const float* __restrict__ dh, const float* __restrict__ x, long long R, int N, int C,
+                       const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ pe, int C0,
+                       long long pe_bstride, float posw, const float* __restrict__ mask, float drop_p,
+                       unsigned long long seed, const float* __restrict__ stats, float* __restrict__ dx,
+                       float* __restrict__ dt_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (long long r = (long long)blockIdx.x * FAST_WARPS + warp; r < R; r += (long long)gridDim.x * FAST_WARPS) {
+    const float m1 = stats[r * 4 + 0], r1 = stats[r * 4 + 1], m2 = stats[r * 4 + 2], r2 = stats[r * 4 + 3];
+    const long long bi = r / N, ni = r % N;
+    const float* per = pe + bi * pe_bstride + ni * C0;
+    const float mk = mask ? mask[r] : 1.f;
+    float4 a[NV], yh[NV], d[NV];
+    row_load<NV>(a, x + r * C, C, lane);
+    row_load<NV>(d, dh + r * C, C, lane);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * lane + 128 * i;
+      yh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C) {
+        const float4 gg = ld4(g + c), bb = ld4(b + c), pp = ld4(per + c);
+        a[i].x = (a[i].x - m1) * r1; a[i].y = (a[i].y - m1) * r1; a[i].z = (a[i].z - m1) * r1; a[i].w = (a[i].w - m1) * r1;
+        yh[i].x = (a[i].x * gg.x + bb.x + posw * pp.x - m2) * r2; yh[i].y = (a[i].y * gg.y + bb.y + posw * pp.y - m2) * r2;
+        yh[i].z = (a[i].z * gg.z + bb.z + posw * pp.z - m2) * r2; yh[i].w = (a[i].w * gg.w + bb.w + posw * pp.w - m2) * r2;
+        d[i].x *= mk; d[i].y *= mk; d[i].z *= mk; d[i].w *= mk;
+        if (drop_p > 0.f) d[i] = drop4(d[i], drop_p, keep_scale, seed, (unsigned long long)(r * C + c));
+        s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+        s2 += (d[i].x * yh[i].x + d[i].y * yh[i].y) + (d[i].z * yh[i].z + d[i].w * yh[i].w);
+      }
+    }
+    s1 = sx::warp_sum(s1) / C; s2 = sx::warp_sum(s2) / C;
+    float s3 = 0.f, s4 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * lane + 128 * i;
+      if (c < C) {
+        const float4 gg = ld4(g + c);
+        float4 dt;
+        dt.x = r2 * (d[i].x - s1 - yh[i].x * s2); dt.y = r2 * (d[i].y - s1 - yh[i].y * s2);
+        dt.z = r2 * (d[i].z - s1 - yh[i].z * s2); dt.w = r2 * (d[i].w - s1 - yh[i].w * s2);
+        *reinterpret_cast<float4*>(dt_out + r * C + c) = dt;
+        d[i] = make_float4(dt.x * gg.x, dt.y * gg.y, dt.z * gg.z, dt.w * gg.w);
+        s3 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+        s4 += (d[i].x * a[i].x + d[i].y * a[i].y) + (d[i].z * a[i].z + d[i].w * a[i].w);
+      }
+    }
+    s3 = sx::warp_sum(s3) / C; s4 = sx::warp_sum(s4) / C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * lane + 128 * i;
+      if (c < C) {
+        float4 o;
+        o.x = r1 * (d[i].x - s3 - a[i].x * s4); o.y = r1 * (d[i].y - s3 - a[i].y * s4);
+        o.z = r1 * (d[i].z - s3 - a[i].z * s4); o.w = r1 * (d[i].w - s3 - a[i].w * s4);
+        *reinterpret_cast<float4*>(dx + r * C + c) = o;
+      }
+    }
+  }
+}
+
+// column part of a LayerNorm-type backward:  dg[c] += sum_r dy[r,c] * (x[r,c]-mean_r)*rstd_r ; db[c] += sum_r dy[r,c]
+// stats rows have `sstride` floats with mean/rstd at offsets 0/1.  block (32 lanes x 8 row slots), lane owns 4 columns.
+__global__ void __launch_bounds__(256)
+ln_param_grad_cols_fast(const float* __restrict__ dy, const float* __restrict__ x, long long R, int C,
+                        const float* __restrict__ stats, int sstride, float* __restrict__ dg, float* __restrict__ db) {
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+  if (c < C)
+    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < R; r += (long long)gridDim.y * 8) {
+      const float mean = stats[r * sstride], rstd = stats[r * sstride + 1];
+      const float4 v = ld4(x + r * C + c), d = ld4(dy + r * C + c);
+      ag.x += d.x * (v.x - mean) * rstd; ag.y += d.y * (v.y - mean) * rstd;
+      ag.z += d.z * (v.z - mean) * rstd; ag.w += d.w * (v.w - mean) * rstd;
+      ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+    }
+  __shared__ float4 s[2][8][32];
+  s[0][threadIdx.y][threadIdx.x] = ag; s[1][threadIdx.y][threadIdx.x] = ab;
+  __syncthreads();
+  if (threadIdx.y < 2 && c < C) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = 0; y < 8; ++y) {
+      const float4 u = s[threadIdx.y][y][threadIdx.x];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    float* dst = threadIdx.y == 0 ? dg : db;
+    atomicAdd(dst + c, t.x); atomicAdd(dst + c + 1, t.y); atomicAdd(dst + c + 2, t.z); atomicAdd(dst + c + 3, t.w);
+  }
+}
+
+// dpe[(b*bstride) + n*C0 + c] += posw * sum over the batch (shared code) or the sample itself (per-sample code) of dt
+__global__ void pos_grad_from_dt_fast(const float* __restrict__ dt, int B, int N, int C, int C0, long long pe_bstride,
+                                      float posw, float* __restrict__ dpe) {
+  const long long total = (long long)N * (C / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / (C / 4);
+    const int c = (int)(i % (C / 4)) * 4;
+    if (pe_bstride == 0) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int bi = 0; bi < B; ++bi) {
+        const float4 v = ld4(dt + ((long long)bi * N + n) * C + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      float4* o = reinterpret_cast<float4*>(dpe + n * C0 + c);
+      float4 cur = *o;
+      cur.x += posw * acc.x; cur.y += posw * acc.y; cur.z += posw * acc.z; cur.w += posw * acc.w;
+      *o = cur;
+    } else {
+      for (int bi = 0; bi < B; ++bi) {
+        const float4 v = ld4(dt + ((long long)bi * N + n) * C + c);
+        float4* o = reinterpret_cast<float4*>(dpe + bi * pe_bstride + n * C0 + c);
+        float4 cur = *o;
+        cur.x += posw * v.x; cur.y += posw * v.y; cur.z += posw * v.z; cur.w += posw * v.w;
+        *o = cur;
+      }
+    }
+  }
+}
+
+// LayerNorm (affine) backward, row part: dx only
+template <int NV>
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+layernorm_bwd_rows_fast(const float* __restrict__ dy, const float* __restrict__ x, long long R, int C,
+                        const float* __restrict__ g, const float* __restrict__ stats, float* __restrict__ dx, int rnd) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * FAST_WARPS + warp; r < R; r += (long long)gridDim.x * FAST_WARPS) {
+    const float m = stats[r * 2], rs = stats[r * 2 + 1];
+    float4 a[NV], d[NV];
+    row_load<NV>(a, x + r * C, C, lane);
+    row_load<NV>(d, dy + r * C, C, lane);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * lane + 128 * i;
+      if (c < C) {
+        const float4 gg = ld4(g + c);
+        a[i].x = (a[i].x - m) * rs; a[i].y = (a[i].y - m) * rs; a[i].z = (a[i].z - m) * rs; a[i].w = (a[i].w - m) * rs;
+        d[i].x *= gg.x; d[i].y *= gg.y; d[i].z *= gg.z; d[i].w *= gg.w;
+        s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+        s2 += (d[i].x * a[i].x + d[i].y * a[i].y) + (d[i].z * a[i].z + d[i].w * a[i].w);
+      }
+    }
+    s1 = sx::warp_sum(s1) / C; s2 = sx::warp_sum(s2) / C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * lane + 128 * i;
+      if (c < C) {
+        float4 o;
+        o.x = rs * (d[i].x - s1 - a[i].x * s2); o.y = rs * (d[i].y - s1 - a[i].y * s2);
+        o.z = rs * (d[i].z - s1 - a[i].z * s2); o.w = rs * (d[i].w - s1 - a[i].w * s2);
+        *reinterpret_cast<float4*>(dx + r * C + c) = rnd4(o, rnd);
+      }
+    }
+  }
+}
+
+// launch helpers ---------------------------------------------------------------------------------
+inline int nv_for(int C) { return C <= 256 ? 2 : (C <= 512 ? 4 : (C <= 1024 ? 8 : (C <= 2048 ? 16 : 0))); }
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -401,9 +401,7 @@ class _GroupLinear(torch.autograd.Function):
             dW = dW.view(ctx.wshape)
         if ctx.needs_input_grad[2]:
             db = torch.zeros((M, Fd), device=G.device, dtype=torch.float32)
-            for bi in range(B):
-                for m in range(M):
-                    colsum(dY[bi, m], out=db[m])
+            L.call("sx_colsum_batched", dY.data_ptr(), B, M * N * Fd, M, N * Fd, N, Fd, Fd, db.data_ptr(), _stream())
             db = db.view(-1)
         return dG, dW, db
 
@@ -435,9 +433,10 @@ class _LnSoftAggr(torch.autograd.Function):
         db = torch.zeros_like(g)
         dws = torch.zeros(Fd, device=Y.device, dtype=torch.float32)
         dbs = torch.zeros(1, device=Y.device, dtype=torch.float32)
+        scratch = torch.empty(B * M * N, device=Y.device, dtype=torch.float32)
         L.call("sx_ln_softaggr_bwd", dout.data_ptr(), Y.data_ptr(), B, M, N, Fd, g.data_ptr(), b.data_ptr(),
                ws.data_ptr(), drop_p, seed, stats.data_ptr(), wts.data_ptr(), dY.data_ptr(), L.SX_F32, 1, dg.data_ptr(),
-               db.data_ptr(), dws.data_ptr(), dbs.data_ptr(), _stream())
+               db.data_ptr(), dws.data_ptr(), dbs.data_ptr(), scratch.data_ptr(), _stream())
         return dY, dg, db, dws.view(ws_shape), dbs.view(bs_shape), None, None
 
 
@@ -501,9 +500,10 @@ class _Prologue(torch.autograd.Function):
         dg = torch.zeros_like(g)
         db = torch.zeros_like(b)
         dpe = torch.zeros_like(pe) if ctx.needs_input_grad[3] else None
+        scratch = torch.empty_like(x)
         L.call("sx_prologue_bwd", dh.data_ptr(), x.data_ptr(), B, N, Cd, g.data_ptr(), b.data_ptr(), pe.data_ptr(), C0,
                pe_bstride, posw, _ptr(mask), drop_p, seed, stats.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(),
-               _ptr(dpe), _stream())
+               _ptr(dpe), scratch.data_ptr(), _stream())
         return dx, dg, db, dpe, None, None, None, None
 
 
