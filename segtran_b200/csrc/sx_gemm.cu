@@ -30,9 +30,10 @@ constexpr int A_STAGE_BYTES = BM * BKB;       // 16 KB
 constexpr int B_STAGE_BYTES = BN * BKB;       // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 256;
-constexpr int STG_LD = 36;                   // staging row pitch in floats (16-byte aligned, conflict-free quarter-warps)
-constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;   // one [32][36] fp32 tile per epilogue warp
+constexpr int NUM_THREADS = 384;         // warps 0-3: TMA / MMA / TMEM alloc / idle;  warps 4-11: epilogue (2 per lane quarter)
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int STG_LD = 32;                   // staging tile [32][32] fp32 per epilogue warp, 16-byte chunks XOR-swizzled by row
+constexpr int STG_BYTES = NUM_EPI_WARPS * 32 * STG_LD * 4;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STG_BYTES;
 
 struct GemmParams {
@@ -108,7 +109,7 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       sx::mbar_init(&tfull_bar[a], 1);
-      sx::mbar_init(&tempty_bar[a], 4);
+      sx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
     }
     sx::fence_barrier_init();
   }
@@ -129,6 +130,8 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     z1 = t / p.Z0;
   };
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");      // warpgroup 0 hands its registers over
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (sx::elect_one()) {
@@ -209,13 +212,16 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");   // warpgroups 1-2: epilogue
     // ===================== epilogue =====================
     // TMEM -> registers (one accumulator row per thread) -> bias/act/dropout/rounding -> per-warp shared-memory
     // staging tile [32 rows][32 cols] -> row-contiguous global stores: every warp store instruction writes four
     // full 128-byte row segments instead of 32 scattered 16-byte pieces.
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
-    float* stg = stage_base + q * (32 * STG_LD);
+    const int half = (warp - 4) >> 2;           // which half of the column chunks this warp drains
+    float* stg = stage_base + (warp - 4) * (32 * STG_LD);
     int it = 0;
     float tmax = -3.0e38f;
     const int sr = lane >> 3, sc = (lane & 7) * 4;      // cooperative-store coordinates inside the staging tile
@@ -223,7 +229,8 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto coop_store = [&](void* base, const float (&f)[32], long long zoff, int row0, int col0, bool atomic_add) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(stg + lane * STG_LD + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        *reinterpret_cast<float4*>(stg + lane * STG_LD + (((j >> 2) ^ (lane & 7)) << 2)) =
+            make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
       __syncwarp();
 #pragma unroll
       for (int rr = 0; rr < 32; rr += 4) {
@@ -231,7 +238,7 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int grow = row0 + r;
         const int col = col0 + sc;
         if (grow < p.M && col < p.N) {
-          const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_LD + sc);
+          const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_LD + ((((sc >> 2) ^ (r & 7))) << 2));
           const long long off = zoff + (long long)grow * p.ldc + col;
           const bool full4 = (col + 3 < p.N) && p.c_vec_ok;
           if (p.c_bf16) {
@@ -283,7 +290,7 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float bias_m = (add_bias && p.bias_mode == SX_BIAS_M && row_ok) ? bias[row] : 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int col0 = nb * BN + c * 32;
         if (col0 >= p.N) break;                 // warp-uniform
         uint32_t v[32];

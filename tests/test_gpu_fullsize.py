@@ -88,3 +88,39 @@ def test_cfg4_head_linearity_and_crop_parity():
     with torch.no_grad():
         y = head(cs.cuda(), vs.cuda(), (2, 2, 2), (16, 16, 16))
     assert rel_err(y, ref) < 1e-4
+
+
+@pytest.mark.parametrize("dims,A,grid,qkb", [
+    ([1792, 1792, 896, 448], 256, (36, 36), False),      # cfg 2 stack (eff-b4, layercompress 1,1,2,2, --noqkbias), 36x36 grid
+    ([2048, 2048, 2048], 256, (22, 22), True),           # cfg 3 stack (resnet50, 2 layers), quarter-size grid
+])
+def test_2d_config_stacks_match_oracle(dims, A, grid, qkb):
+    """The 2-D BASELINE configs' channel widths (1792/896/448/2048, d = 448/224/512) at a reduced token grid."""
+    import segtran_b200.networks.segtran_shared as S
+    cfg = encoder_config(S.SegtranConfig, dims=dims, num_modes=4, num_attractors=A, pos_dim=2, qk_have_bias=qkb)
+    cfg.translayer_compress_ratios = [1] * len(dims)
+    torch.manual_seed(5)
+    enc = S.SegtranFusionEncoder(cfg, "Fusion")
+    init = S.SegtranInitWeights(cfg)
+    enc.apply(init.init_weights)
+    enc.apply(init.tie_qk)
+    enc.apply(init.add_identity_bias)
+    enc.eval()
+    p = {"voxel_fusion." + k: v.clone() for k, v in enc.state_dict().items()}
+    N = grid[0] * grid[1]
+    x = torch.randn(2, N, dims[0])
+    pos = O.voxels_pos_for_grid(grid, (8, 8), 2)
+    mask = (torch.rand(2, N, 1) > 0.1).float()
+    with torch.no_grad():
+        ref = O.fusion_encoder(p, "voxel_fusion.", x, pos, mask, dims, 4)
+        y = enc.cuda()(x.cuda(), pos.cuda(), mask.cuda(), torch.Size(grid))
+    e = rel_err(y, ref)
+    print("dims %s: max-rel %.3e rms-rel %.3e" % (dims, e, rms_rel(y, ref)))
+    assert e < 1e-3
+    # gradients flow and are finite at these widths
+    xg = x.cuda().requires_grad_()
+    enc.train()
+    yg = enc(xg, pos.cuda(), mask.cuda(), torch.Size(grid))
+    yg.square().mean().backward()
+    assert torch.isfinite(xg.grad).all()
+    assert all(torch.isfinite(q.grad).all() for q in enc.parameters() if q.grad is not None)
