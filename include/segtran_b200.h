@@ -84,9 +84,17 @@ typedef struct {
   float drop_p;                  /* dropout on the stored value (after act); 0 disables */
   uint32_t _pad3;
   uint64_t drop_seed;            /* counter-based mask: keep(idx) = hash(seed, flat index in C) >= p */
+  const uint64_t* drop_seed_dev; /* optional device seed added to drop_seed (CUDA-graph safe) */
 } sx_gemm_args;
 
 int sx_gemm(const sx_gemm_args* args, void* stream);
+
+/* Dropout seeds: every dropout-capable entry takes `seed` (by value) and `seed_dev` (device pointer or NULL); the
+ * effective seed is seed + *seed_dev, read on the device in stream order, so a captured CUDA graph draws a new mask
+ * on every replay.  sx_seed_derive writes out[0] = base[0] + add (the per-call seed an op keeps for its backward);
+ * sx_seed_advance bumps the base seed once per training step. */
+int sx_seed_derive(const uint64_t* base, uint64_t add, uint64_t* out, void* stream);
+int sx_seed_advance(uint64_t* base, uint64_t inc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Row-wise kernels (HBM-bound).  "act dtype" arguments are SX_F32 | SX_BF16; round_tf32 rounds fp32
@@ -109,12 +117,12 @@ int sx_pos_lsinu_bwd(const float* pos, const float* posmax, int64_t R, int32_t p
  *   h = mask * dropout( LN( LN_{g,b}(x) + posw * pe[..., :C] ) ),  x [B,N,C] fp32, pe rows of length C0,
  *   pe_bstride = 0 when the code is shared by the batch; mask [B*N] fp32 or NULL; stats [B*N,4]. */
 int sx_prologue_fwd(const float* x, int64_t B, int32_t N, int32_t C, const float* g, const float* b, const float* pe,
-                    int32_t C0, int64_t pe_bstride, float posw, const float* mask, float drop_p, uint64_t seed, void* h,
+                    int32_t C0, int64_t pe_bstride, float posw, const float* mask, float drop_p, uint64_t seed, const uint64_t* seed_dev, void* h,
                     int32_t h_dtype, int32_t round_tf32, float* stats, void* stream);
 /* dh fp32 -> dx [B,N,C]; dg, db [C] and dpe (same addressing as pe, may be NULL) are accumulated (+=). */
 int sx_prologue_bwd(const float* dh, const float* x, int64_t B, int32_t N, int32_t C, const float* g, const float* b,
                     const float* pe, int32_t C0, int64_t pe_bstride, float posw, const float* mask, float drop_p,
-                    uint64_t seed, const float* stats, float* dx, float* dg, float* db, float* dpe,
+                    uint64_t seed, const uint64_t* seed_dev, const float* stats, float* dx, float* dg, float* db, float* dpe,
                     float* dt_scratch /* [B*N*C] or NULL */, void* stream);
 
 /* Row softmax with the reference's conditional clamp and attention dropout (segtran_shared.py:578-580, :601-605):
@@ -123,10 +131,10 @@ int sx_prologue_bwd(const float* dh, const float* x, int64_t B, int32_t N, int32
  *   diag (optional, device float[2]): [0] = running max of *amax, [1] += 1 when the clamp fired — the module's
  *   max_attn / clamp_count counters (:575-587) without the reference's two .item() host syncs per call. */
 int sx_softmax_fwd(const float* S, int64_t R, int32_t L, int64_t lds, const float* amax, float clip, float drop_p,
-                   uint64_t seed, void* P, int32_t p_dtype, int64_t ldp, int32_t round_tf32, float* lse, float* diag,
+                   uint64_t seed, const uint64_t* seed_dev, void* P, int32_t p_dtype, int64_t ldp, int32_t round_tf32, float* lse, float* diag,
                    void* stream);
 int sx_softmax_bwd(const float* dP, int64_t ldd, const float* S, int64_t lds, const float* lse, int64_t R, int32_t L,
-                   const float* amax, float clip, float drop_p, uint64_t seed, int64_t ldp_fwd, void* dS,
+                   const float* amax, float clip, float drop_p, uint64_t seed, const uint64_t* seed_dev, int64_t ldp_fwd, void* dS,
                    int32_t ds_dtype, int64_t ldo, int32_t round_tf32, void* stream);
 
 /* LayerNorm with affine over rows, eps 1e-12 (first_norm_layer, segtran_shared.py:456).  stats [R,2]. */
@@ -139,15 +147,15 @@ int sx_layernorm_bwd(const float* dy, const float* x, int64_t R, int32_t C, cons
  *   Yn = LN_{g,b}(dropout(Y));  w = softmax_modes(Yn.ws + bs);  out = sum_m w_m Yn_m
  *   Y [B,M,N,F] fp32 -> out [B,N,F] fp32; stats [B,M,N,2]; wts [B,M,N]. */
 int sx_ln_softaggr_fwd(const float* Y, int32_t B, int32_t M, int32_t N, int32_t F, const float* g, const float* b,
-                       const float* ws, const float* bs, float drop_p, uint64_t seed, float* out, float* stats,
+                       const float* ws, const float* bs, float drop_p, uint64_t seed, const uint64_t* seed_dev, float* out, float* stats,
                        float* wts, void* stream);
 int sx_ln_softaggr_bwd(const float* dout, const float* Y, int32_t B, int32_t M, int32_t N, int32_t F, const float* g,
-                       const float* b, const float* ws, float drop_p, uint64_t seed, const float* stats,
+                       const float* b, const float* ws, float drop_p, uint64_t seed, const uint64_t* seed_dev, const float* stats,
                        const float* wts, void* dY, int32_t dy_dtype, int32_t round_tf32, float* dg, float* db,
                        float* dws, float* dbs, float* dscore_scratch /* [B*M*N] or NULL */, void* stream);
 
 /* dH = dropout'(dG) * gelu'(H)  (MMSharedMid backward, segtran_shared.py:243-245) */
-int sx_gelu_bwd(const float* dG, const void* H, int32_t h_dtype, int64_t n, float drop_p, uint64_t seed, void* dH,
+int sx_gelu_bwd(const float* dG, const void* H, int32_t h_dtype, int64_t n, float drop_p, uint64_t seed, const uint64_t* seed_dev, void* dH,
                 int32_t dh_dtype, int32_t round_tf32, void* stream);
 /* dtype conversion / TF32 rounding of a flat buffer (weights once per step) */
 int sx_convert(const void* x, int32_t x_dtype, int64_t n, void* y, int32_t y_dtype, int32_t round_tf32, void* stream);

@@ -32,9 +32,7 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 384;         // warps 0-3: TMA / MMA / TMEM alloc / idle;  warps 4-11: epilogue (2 per lane quarter)
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int STG_LD = 32;                   // staging tile [32][32] fp32 per epilogue warp, 16-byte chunks XOR-swizzled by row
-constexpr int STG_BYTES = NUM_EPI_WARPS * 32 * STG_LD * 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STG_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct GemmParams {
   int M, N, K, Z0, Z1;
@@ -55,8 +53,11 @@ struct GemmParams {
   float* amax;
   float drop_p;
   unsigned long long drop_seed;
+  const unsigned long long* drop_seed_dev;
   // descriptor fields (bring-up knobs; defaults are the canonical encodings)
   unsigned int lbo_k, sbo_k, lbo_mn_a, lbo_mn_b, sbo_mn, desc_version;
+  int dbg_epi;      // bring-up: 0 normal, 1 skip global stores, 2 skip TMEM loads too
+  int stream_out;   // output larger than half the L2: store with evict-first (st.global.cs), keep operands (evict-last)
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
@@ -93,7 +94,6 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]       MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]     epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* stage_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -137,6 +137,9 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (sx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      // operand tiles are re-read by every CTA of the same tile row / column: keep them in L2 while a large
+      // output streams through
+      const uint64_t pol = p.stream_out ? sx::kEvictLast : sx::kEvictNormal;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         int z0, z1, mb, nb, ks;
         decode(t, z0, z1, mb, nb, ks);
@@ -151,18 +154,18 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + A_STAGE_BYTES;
           const int k0 = kb * BK;
           if constexpr (!A_MN) {
-            sx::tma_load_4d(sa, &tmA, &full_bar[stage], k0, mb * BM, az0, az1);
+            sx::tma_load_4d(sa, &tmA, &full_bar[stage], k0, mb * BM, az0, az1, pol);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / MN_BOX; ++j)
-              sx::tma_load_4d(sa + j * MN_BOX_BYTES, &tmA, &full_bar[stage], mb * BM + j * MN_BOX, k0, az0, az1);
+              sx::tma_load_4d(sa + j * MN_BOX_BYTES, &tmA, &full_bar[stage], mb * BM + j * MN_BOX, k0, az0, az1, pol);
           }
           if constexpr (!B_MN) {
-            sx::tma_load_4d(sb, &tmB, &full_bar[stage], k0, nb * BN, bz0, bz1);
+            sx::tma_load_4d(sb, &tmB, &full_bar[stage], k0, nb * BN, bz0, bz1, pol);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / MN_BOX; ++j)
-              sx::tma_load_4d(sb + j * MN_BOX_BYTES, &tmB, &full_bar[stage], nb * BN + j * MN_BOX, k0, bz0, bz1);
+              sx::tma_load_4d(sb + j * MN_BOX_BYTES, &tmB, &full_bar[stage], nb * BN + j * MN_BOX, k0, bz0, bz1, pol);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -216,61 +219,53 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");   // warpgroups 1-2: epilogue
     // ===================== epilogue =====================
-    // TMEM -> registers (one accumulator row per thread) -> bias/act/dropout/rounding -> per-warp shared-memory
-    // staging tile [32 rows][32 cols] -> row-contiguous global stores: every warp store instruction writes four
-    // full 128-byte row segments instead of 32 scattered 16-byte pieces.
+    // TMEM -> registers in the 16x256b fragment distribution (thread t: rows t/4 and t/4+8 of each 16-lane half,
+    // column pairs 8j+2(t%4)) -> bias / GELU / dropout / TF32 rounding -> direct 8-byte global stores.  Four
+    // neighbouring lanes write one complete 32-byte sector, so there is no shared-memory transposition (the UMMA
+    // operand fetch already uses ~3/4 of the shared-memory bandwidth) and no partial-sector write.
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;           // which half of the column chunks this warp drains
-    float* stg = stage_base + (warp - 4) * (32 * STG_LD);
     int it = 0;
     float tmax = -3.0e38f;
-    const int sr = lane >> 3, sc = (lane & 7) * 4;      // cooperative-store coordinates inside the staging tile
+    const int tr = lane >> 2;                   // row within an 8-row group
+    const int tc = (lane & 3) * 2;              // first column of this thread's pair within an 8-column group
 
-    auto coop_store = [&](void* base, const float (&f)[32], long long zoff, int row0, int col0, bool atomic_add) {
+    // f index: [P][j][h][e] -> 16*P + 4*j + 2*h + e ; row = row0 + 16P + 8h + tr ; col = col0 + 8j + tc + e
+    auto store_frag = [&](void* base, const float (&f)[32], long long zoff, int row0, int col0, bool atomic_add) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(stg + lane * STG_LD + (((j >> 2) ^ (lane & 7)) << 2)) =
-            make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-      __syncwarp();
+      for (int P = 0; P < 2; ++P)
 #pragma unroll
-      for (int rr = 0; rr < 32; rr += 4) {
-        const int r = rr + sr;
-        const int grow = row0 + r;
-        const int col = col0 + sc;
-        if (grow < p.M && col < p.N) {
-          const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_LD + ((((sc >> 2) ^ (r & 7))) << 2));
-          const long long off = zoff + (long long)grow * p.ldc + col;
-          const bool full4 = (col + 3 < p.N) && p.c_vec_ok;
-          if (p.c_bf16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(base) + off;
-            if (full4) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-              uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&h0);
-              pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              *reinterpret_cast<uint2*>(o) = pk;
-            } else {
-              const float e[4] = {v.x, v.y, v.z, v.w};
-              for (int u = 0; u < 4; ++u)
-                if (col + u < p.N) o[u] = __float2bfloat16_rn(e[u]);
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(base) + off;
-            if (atomic_add) {
-              const float e[4] = {v.x, v.y, v.z, v.w};
-              for (int u = 0; u < 4; ++u)
-                if (col + u < p.N) atomicAdd(o + u, e[u]);
-            } else if (full4) {
-              *reinterpret_cast<float4*>(o) = v;
-            } else {
-              const float e[4] = {v.x, v.y, v.z, v.w};
-              for (int u = 0; u < 4; ++u)
-                if (col + u < p.N) o[u] = e[u];
+        for (int h = 0; h < 2; ++h) {
+          const int grow = row0 + 16 * P + 8 * h + tr;
+          if (grow < p.M) {
+            const long long roff_ = zoff + (long long)grow * p.ldc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col = col0 + 8 * j + tc;
+              const float a = f[16 * P + 4 * j + 2 * h], b = f[16 * P + 4 * j + 2 * h + 1];
+              if (col + 1 < p.N) {
+                if (p.c_bf16) {
+                  __nv_bfloat162 hb = __floats2bfloat162_rn(a, b);
+                  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(base) + roff_ + col;
+                  if (p.c_vec_ok) *reinterpret_cast<__nv_bfloat162*>(o) = hb;
+                  else { o[0] = hb.x; o[1] = hb.y; }
+                } else {
+                  float* o = reinterpret_cast<float*>(base) + roff_ + col;
+                  if (atomic_add) { atomicAdd(o, a); atomicAdd(o + 1, b); }
+                  else if (p.c_vec_ok) {
+                    if (p.stream_out) __stcs(reinterpret_cast<float2*>(o), make_float2(a, b));
+                    else *reinterpret_cast<float2*>(o) = make_float2(a, b);
+                  }
+                  else { o[0] = a; o[1] = b; }
+                }
+              } else if (col < p.N) {
+                if (p.c_bf16) reinterpret_cast<__nv_bfloat16*>(base)[roff_ + col] = __float2bfloat16_rn(a);
+                else if (atomic_add) atomicAdd(reinterpret_cast<float*>(base) + roff_ + col, a);
+                else reinterpret_cast<float*>(base)[roff_ + col] = a;
+              }
             }
           }
         }
-      }
-      __syncwarp();
     };
 
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -281,60 +276,95 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       sx::mbar_wait(&tfull_bar[acc], acc_phase);
       sx::tc_fence_after();
       const int row0 = mb * BM + q * 32;
-      const int row = row0 + lane;
-      const bool row_ok = row < p.M;
       const long long zoff = (long long)z1 * p.c_sz1 + (long long)z0 * p.c_sz0;
-      const long long roff = zoff + (long long)row * p.ldc;
       const float* bias = p.bias ? p.bias + (long long)z1 * p.bias_sz1 + (long long)z0 * p.bias_sz0 : nullptr;
       const bool add_bias = (bias != nullptr) && (ks == 0);
-      const float bias_m = (add_bias && p.bias_mode == SX_BIAS_M && row_ok) ? bias[row] : 0.f;
+      float bias_m[4] = {0.f, 0.f, 0.f, 0.f};              // [P][h]
+      if (add_bias && p.bias_mode == SX_BIAS_M) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = row0 + 16 * (i >> 1) + 8 * (i & 1) + tr;
+          bias_m[i] = r < p.M ? bias[r] : 0.f;
+        }
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         const int col0 = nb * BN + c * 32;
         if (col0 >= p.N) break;                 // warp-uniform
-        uint32_t v[32];
-        sx::tmem_ld32(taddr + c * 32, v);
+        if (p.dbg_epi == 2) continue;
+        uint32_t va[16], vb[16];
+        sx::tmem_ld_16x256b_x4(taddr + c * 32, va);
+        sx::tmem_ld_16x256b_x4(taddr + c * 32 + (16u << 16), vb);
         sx::tmem_ld_wait();
+        if (p.dbg_epi == 1) continue;
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha + bias_m;
-        if (add_bias && p.bias_mode == SX_BIAS_N) {
-          const float bj = (col0 + lane < p.N) ? bias[col0 + lane] : 0.f;     // one coalesced load, then broadcast
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __shfl_sync(0xffffffffu, bj, j);
+        for (int i = 0; i < 16; ++i) {
+          f[i] = __uint_as_float(va[i]) * p.alpha + bias_m[(i >> 1) & 1];
+          f[16 + i] = __uint_as_float(vb[i]) * p.alpha + bias_m[2 + ((i >> 1) & 1)];
         }
-        if (p.preact) coop_store(p.preact, f, zoff, row0, col0, false);
+        if (add_bias && p.bias_mode == SX_BIAS_N) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = col0 + 8 * j + tc;
+            const float b0 = col < p.N ? bias[col] : 0.f, b1 = col + 1 < p.N ? bias[col + 1] : 0.f;
+#pragma unroll
+            for (int P = 0; P < 2; ++P)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                f[16 * P + 4 * j + 2 * h] += b0;
+                f[16 * P + 4 * j + 2 * h + 1] += b1;
+              }
+          }
+        }
+        if (p.preact) store_frag(p.preact, f, zoff, row0, col0, false);
         if (p.act == SX_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = sx::gelu_erf(f[j]);
+          for (int i = 0; i < 32; ++i) f[i] = sx::gelu_erf(f[i]);
         }
         if (p.drop_p > 0.f) {
           const float keep_scale = 1.f / (1.f - p.drop_p);
           const uint32_t p16 = sx::drop_p16(p.drop_p);
-          const unsigned long long e0 = (unsigned long long)(roff + col0);
-          if ((e0 & 3ull) == 0) {
+          const unsigned long long dseed = p.drop_seed + (p.drop_seed_dev ? *p.drop_seed_dev : 0ull);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const uint2 h = sx::drop_hash(p.drop_seed, (e0 + j) >> 2);
+          for (int P = 0; P < 2; ++P)
 #pragma unroll
-              for (int u = 0; u < 4; ++u) f[j + u] = sx::drop_keep(h, u, p16) ? f[j + u] * keep_scale : 0.f;
+            for (int h = 0; h < 2; ++h) {
+              const long long rbase = zoff + (long long)(row0 + 16 * P + 8 * h + tr) * p.ldc;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const unsigned long long e0 = (unsigned long long)(rbase + col0 + 8 * j + tc);
+                const uint2 hsh = sx::drop_hash(dseed, e0 >> 2);
+                const int i0 = 16 * P + 4 * j + 2 * h;
+                if ((e0 & 1ull) == 0) {         // the pair lies inside one 4-element hash group
+                  f[i0] = sx::drop_keep(hsh, (int)(e0 & 3), p16) ? f[i0] * keep_scale : 0.f;
+                  f[i0 + 1] = sx::drop_keep(hsh, (int)(e0 & 3) + 1, p16) ? f[i0 + 1] * keep_scale : 0.f;
+                } else {
+                  f[i0] = sx::drop_keep1(dseed, e0, p16) ? f[i0] * keep_scale : 0.f;
+                  f[i0 + 1] = sx::drop_keep1(dseed, e0 + 1, p16) ? f[i0 + 1] * keep_scale : 0.f;
+                }
+              }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = sx::drop_keep1(p.drop_seed, e0 + j, p16) ? f[j] * keep_scale : 0.f;
-          }
         }
         if (p.round_tf32 && !p.c_bf16) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = sx::round_tf32(f[j]);
+          for (int i = 0; i < 32; ++i) f[i] = sx::round_tf32(f[i]);
         }
-        if (p.amax && row_ok) {
+        if (p.amax) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) tmax = fmaxf(tmax, f[j]);
+          for (int P = 0; P < 2; ++P)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (row0 + 16 * P + 8 * h + tr < p.M) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                  for (int e = 0; e < 2; ++e)
+                    if (col0 + 8 * j + tc + e < p.N) tmax = fmaxf(tmax, f[16 * P + 4 * j + 2 * h + e]);
+              }
         }
-        coop_store(p.C, f, zoff, row0, col0, p.accumulate != 0);
+        store_frag(p.C, f, zoff, row0, col0, p.accumulate != 0);
       }
       sx::tc_fence_before();
       __syncwarp();
@@ -378,6 +408,8 @@ struct DebugKnobs {
   long long lbo_k = 16, sbo_k = 1024, sbo_mn = -1, desc_version = 1;   // sbo_mn -1: canonical (1024 B; 512 B for tf32)
   long long lbo_mn_a = -1, lbo_mn_b = -1;     // -1: canonical (BK rows * 128 B)
   long long max_ctas = -1;
+  long long dbg_epi = 0;
+  long long stream_out = -1;      // -1: automatic
 };
 DebugKnobs g_knobs;
 
@@ -458,6 +490,8 @@ extern "C" int sx_gemm_debug_set(const char* key, int64_t value) {
   else if (k == "lbo_mn_b") g_knobs.lbo_mn_b = value;
   else if (k == "desc_version") g_knobs.desc_version = value;
   else if (k == "max_ctas") g_knobs.max_ctas = value;
+  else if (k == "dbg_epi") g_knobs.dbg_epi = value;
+  else if (k == "stream_out") g_knobs.stream_out = value;
   else {
     sx_set_error("sx_gemm_debug_set: unknown key %s", key);
     return -1;
@@ -496,18 +530,23 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
   p.b_uses_z0 = a->B.stride_z0 != 0; p.b_uses_z1 = a->B.stride_z1 != 0;
   p.C = a->C; p.c_bf16 = a->c_dtype == SX_BF16; p.round_tf32 = a->round_tf32;
   p.ldc = a->ldc; p.c_sz0 = a->c_stride_z0; p.c_sz1 = a->c_stride_z1;
-  const int vec = 4;
-  p.c_vec_ok = ((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && (a->ldc % vec == 0) && (a->c_stride_z0 % vec == 0) &&
-               (a->c_stride_z1 % vec == 0) &&
-               (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0);
+  // the epilogue stores column pairs (8 bytes fp32 / 4 bytes bf16): pairs must stay naturally aligned
+  p.c_vec_ok = ((reinterpret_cast<uintptr_t>(a->C) & 7) == 0) && (a->ldc % 2 == 0) && (a->c_stride_z0 % 2 == 0) &&
+               (a->c_stride_z1 % 2 == 0) && (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 7) == 0);
   p.alpha = a->alpha; p.bias_mode = a->bias ? a->bias_mode : SX_BIAS_NONE; p.bias = a->bias;
   p.bias_sz0 = a->bias_stride_z0; p.bias_sz1 = a->bias_stride_z1;
   p.act = a->act; p.accumulate = a->accumulate; p.preact = a->preact; p.amax = a->amax;
   p.drop_p = a->drop_p; p.drop_seed = a->drop_seed;
+  p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(a->drop_seed_dev);
   p.lbo_k = (unsigned)g_knobs.lbo_k; p.sbo_k = (unsigned)g_knobs.sbo_k; p.sbo_mn = (unsigned)(g_knobs.sbo_mn >= 0 ? g_knobs.sbo_mn : (es == 4 ? 512 : 1024));
   p.lbo_mn_a = (unsigned)(g_knobs.lbo_mn_a >= 0 ? g_knobs.lbo_mn_a : bk * BKB);
   p.lbo_mn_b = (unsigned)(g_knobs.lbo_mn_b >= 0 ? g_knobs.lbo_mn_b : bk * BKB);
   p.desc_version = (unsigned)g_knobs.desc_version;
+  p.dbg_epi = (int)g_knobs.dbg_epi;
+  {
+    const double out_bytes = (double)a->M * a->N * a->Z0 * a->Z1 * (p.c_bf16 ? 2 : 4) * (a->preact ? 2 : 1);
+    p.stream_out = g_knobs.stream_out >= 0 ? (int)g_knobs.stream_out : (out_bytes > 64.0 * 1024 * 1024);
+  }
 
   CUtensorMap ta, tb;
   int rc = make_map(&ta, a->A, es, a->M, a->K, a->Z0, a->Z1, BM, "A");

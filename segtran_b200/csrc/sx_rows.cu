@@ -140,7 +140,8 @@ template <typename T>
 __global__ void prologue_fwd_kernel(const float* __restrict__ x, long long R, int N, int C, const float* __restrict__ g,
                                     const float* __restrict__ b, const float* __restrict__ pe, int C0,
                                     long long pe_bstride, float posw, const float* __restrict__ mask, float drop_p,
-                                    unsigned long long seed, T* __restrict__ h, float* __restrict__ stats, int rnd) {
+                                    unsigned long long seed, const unsigned long long* __restrict__ seed_dev, T* __restrict__ h, float* __restrict__ stats, int rnd) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* row = sm + warp * C;
@@ -176,9 +177,10 @@ __global__ void prologue_fwd_kernel(const float* __restrict__ x, long long R, in
 __global__ void prologue_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ x, long long R, int N,
                                     int C, const float* __restrict__ g, const float* __restrict__ b,
                                     const float* __restrict__ pe, int C0, long long pe_bstride, float posw,
-                                    const float* __restrict__ mask, float drop_p, unsigned long long seed,
+                                    const float* __restrict__ mask, float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
                                     const float* __restrict__ stats, float* __restrict__ dx, float* __restrict__ dg,
                                     float* __restrict__ db, float* __restrict__ dpe) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sdg = sm;                       // [C] block accumulators
@@ -233,9 +235,10 @@ __global__ void prologue_bwd_kernel(const float* __restrict__ dh, const float* _
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void softmax_fwd_kernel(const float* __restrict__ S, long long R, int L, long long lds,
-                                   const float* __restrict__ amax, float clip, float drop_p, unsigned long long seed,
+                                   const float* __restrict__ amax, float clip, float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
                                    T* __restrict__ P, long long ldp, float* __restrict__ lse, int rnd,
                                    float* __restrict__ diag) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   extern __shared__ float sm[];
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -275,8 +278,9 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ S, long long R, int
 template <typename T>
 __global__ void softmax_bwd_kernel(const float* __restrict__ dP, long long ldd, const float* __restrict__ S,
                                    long long lds, const float* __restrict__ lse, long long R, int L,
-                                   const float* __restrict__ amax, float clip, float drop_p, unsigned long long seed,
+                                   const float* __restrict__ amax, float clip, float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
                                    long long ldp_fwd, T* __restrict__ dS, long long ldo, int rnd) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   extern __shared__ float sm[];
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -372,8 +376,9 @@ constexpr int MAX_MODES = 8;
 __global__ void ln_softaggr_fwd_kernel(const float* __restrict__ Y, int B, int M, int N, int F,
                                        const float* __restrict__ g, const float* __restrict__ b,
                                        const float* __restrict__ ws, const float* __restrict__ bs, float drop_p,
-                                       unsigned long long seed, float* __restrict__ out, float* __restrict__ stats,
+                                       unsigned long long seed, const unsigned long long* __restrict__ seed_dev, float* __restrict__ out, float* __restrict__ stats,
                                        float* __restrict__ wts) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* rows = sm + (long long)warp * M * F;       // normalised rows of the M modes
@@ -425,10 +430,11 @@ __global__ void ln_softaggr_fwd_kernel(const float* __restrict__ Y, int B, int M
 template <typename T>
 __global__ void ln_softaggr_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ Y, int B, int M,
                                        int N, int F, const float* __restrict__ g, const float* __restrict__ b,
-                                       const float* __restrict__ ws, float drop_p, unsigned long long seed,
+                                       const float* __restrict__ ws, float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
                                        const float* __restrict__ stats, const float* __restrict__ wts,
                                        T* __restrict__ dY, float* __restrict__ dg, float* __restrict__ db,
                                        float* __restrict__ dws, float* __restrict__ dbs, int rnd) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sdg = sm;
@@ -508,7 +514,8 @@ __global__ void ln_softaggr_bwd_kernel(const float* __restrict__ dout, const flo
 // dH = dGd * keep/(1-p) * gelu'(H)   (MMSharedMid backward, segtran_shared.py:243-245)
 template <typename TH, typename TO>
 __global__ void gelu_bwd_kernel(const float* __restrict__ dG, const TH* __restrict__ H, long long n, float drop_p,
-                                unsigned long long seed, TO* __restrict__ dH, int rnd) {
+                                unsigned long long seed, const unsigned long long* __restrict__ seed_dev, TO* __restrict__ dH, int rnd) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float d = dG[i];
@@ -519,7 +526,8 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ dG, const TH* __restri
 
 // fp32 float4 version (n % 4 == 0, 16-byte aligned)
 __global__ void gelu_bwd_f4_kernel(const float4* __restrict__ dG, const float4* __restrict__ H, long long n4, float drop_p,
-                                   unsigned long long seed, float4* __restrict__ dH, int rnd) {
+                                   unsigned long long seed, const unsigned long long* __restrict__ seed_dev, float4* __restrict__ dH, int rnd) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 d = dG[i];
@@ -700,7 +708,7 @@ extern "C" int sx_pos_lsinu_bwd(const float* pos, const float* posmax, int64_t R
 
 extern "C" int sx_prologue_fwd(const float* x, int64_t B, int32_t N, int32_t C, const float* g, const float* b,
                                const float* pe, int32_t C0, int64_t pe_bstride, float posw, const float* mask,
-                               float drop_p, uint64_t seed, void* h, int32_t h_dtype, int32_t round_tf32, float* stats,
+                               float drop_p, uint64_t seed, const uint64_t* seed_dev, void* h, int32_t h_dtype, int32_t round_tf32, float* stats,
                                void* stream) {
   const size_t smem = (size_t)ROW_WARPS * C * 4;
   SX_REQUIRE(smem <= 200 * 1024, "sx_prologue_fwd: C=%d too large", C);
@@ -709,11 +717,11 @@ extern "C" int sx_prologue_fwd(const float* x, int64_t B, int32_t N, int32_t C, 
   if (h_dtype == SX_F32) {
     if (set_smem(prologue_fwd_kernel<float>, smem)) return -2;
     prologue_fwd_kernel<float><<<grid, ROW_WARPS * 32, smem, ST(stream)>>>(
-        x, R, N, C, g, b, pe, C0, pe_bstride, posw, mask, drop_p, seed, (float*)h, stats, round_tf32);
+        x, R, N, C, g, b, pe, C0, pe_bstride, posw, mask, drop_p, seed, (const unsigned long long*)seed_dev, (float*)h, stats, round_tf32);
   } else {
     if (set_smem(prologue_fwd_kernel<__nv_bfloat16>, smem)) return -2;
     prologue_fwd_kernel<__nv_bfloat16><<<grid, ROW_WARPS * 32, smem, ST(stream)>>>(
-        x, R, N, C, g, b, pe, C0, pe_bstride, posw, mask, drop_p, seed, (__nv_bfloat16*)h, stats, 0);
+        x, R, N, C, g, b, pe, C0, pe_bstride, posw, mask, drop_p, seed, (const unsigned long long*)seed_dev, (__nv_bfloat16*)h, stats, 0);
   }
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -721,7 +729,7 @@ extern "C" int sx_prologue_fwd(const float* x, int64_t B, int32_t N, int32_t C, 
 
 extern "C" int sx_prologue_bwd(const float* dh, const float* x, int64_t B, int32_t N, int32_t C, const float* g,
                                const float* b, const float* pe, int32_t C0, int64_t pe_bstride, float posw,
-                               const float* mask, float drop_p, uint64_t seed, const float* stats, float* dx, float* dg,
+                               const float* mask, float drop_p, uint64_t seed, const uint64_t* seed_dev, const float* stats, float* dx, float* dg,
                                float* db, float* dpe, float* dt_scratch, void* stream) {
   if (dt_scratch && C % 4 == 0 && C0 % 4 == 0 && pe_bstride % 4 == 0 && nv_for(C) && al16(dh) && al16(x) && al16(dx) &&
       al16(pe) && al16(g) && al16(b) && al16(dt_scratch) && (!dpe || al16(dpe))) {
@@ -729,7 +737,7 @@ extern "C" int sx_prologue_bwd(const float* dh, const float* x, int64_t B, int32
     const int grid = grid_for_rows(R, FAST_WARPS, sms_cached() * 2);
 #define SX_LAUNCH(NV_)                                                                                                \
   prologue_bwd_rows_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(dh, x, R, N, C, g, b, pe, C0, pe_bstride, posw, \
-                                                                        mask, drop_p, seed, stats, dx, dt_scratch)
+                                                                        mask, drop_p, seed, (const unsigned long long*)seed_dev, stats, dx, dt_scratch)
     switch (nv_for(C)) { case 2: SX_LAUNCH(2); break; case 4: SX_LAUNCH(4); break; case 8: SX_LAUNCH(8); break;
                          default: SX_LAUNCH(16); }
 #undef SX_LAUNCH
@@ -753,7 +761,7 @@ extern "C" int sx_prologue_bwd(const float* dh, const float* x, int64_t B, int32
   if (set_smem(prologue_bwd_kernel, smem)) return -2;
   const long long R = (long long)B * N;
   prologue_bwd_kernel<<<grid_for_rows(R, ROW_WARPS * 4, sms_cached()), ROW_WARPS * 32, smem, ST(stream)>>>(
-      dh, x, R, N, C, g, b, pe, C0, pe_bstride, posw, mask, drop_p, seed, stats, dx, dg, db, dpe);
+      dh, x, R, N, C, g, b, pe, C0, pe_bstride, posw, mask, drop_p, seed, (const unsigned long long*)seed_dev, stats, dx, dg, db, dpe);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -765,12 +773,12 @@ static int softmax_warps(int L, int per_row_floats) {
 }
 
 extern "C" int sx_softmax_fwd(const float* S, int64_t R, int32_t L, int64_t lds, const float* amax, float clip,
-                              float drop_p, uint64_t seed, void* P, int32_t p_dtype, int64_t ldp, int32_t round_tf32,
+                              float drop_p, uint64_t seed, const uint64_t* seed_dev, void* P, int32_t p_dtype, int64_t ldp, int32_t round_tf32,
                               float* lse, float* diag, void* stream) {
   if (p_dtype == SX_F32 && L % 4 == 0 && lds % 4 == 0 && ldp % 4 == 0 && al16(S) && al16(P) && nv_for(L)) {
     const int grid = grid_for_rows(R, FAST_WARPS, sms_cached() * 2);
 #define SX_LAUNCH(NV_)                                                                                          \
-  softmax_fwd_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(S, R, L, lds, amax, clip, drop_p, seed, (float*)P, \
+  softmax_fwd_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(S, R, L, lds, amax, clip, drop_p, seed, (const unsigned long long*)seed_dev, (float*)P, \
                                                                   ldp, lse, round_tf32, diag)
     switch (nv_for(L)) { case 2: SX_LAUNCH(2); break; case 4: SX_LAUNCH(4); break; case 8: SX_LAUNCH(8); break;
                          default: SX_LAUNCH(16); }
@@ -784,11 +792,11 @@ extern "C" int sx_softmax_fwd(const float* S, int64_t R, int32_t L, int64_t lds,
   const int grid = grid_for_rows(R, w, sms_cached());
   if (p_dtype == SX_F32) {
     if (set_smem(softmax_fwd_kernel<float>, smem)) return -2;
-    softmax_fwd_kernel<float><<<grid, w * 32, smem, ST(stream)>>>(S, R, L, lds, amax, clip, drop_p, seed, (float*)P, ldp,
+    softmax_fwd_kernel<float><<<grid, w * 32, smem, ST(stream)>>>(S, R, L, lds, amax, clip, drop_p, seed, (const unsigned long long*)seed_dev, (float*)P, ldp,
                                                                    lse, round_tf32, diag);
   } else {
     if (set_smem(softmax_fwd_kernel<__nv_bfloat16>, smem)) return -2;
-    softmax_fwd_kernel<__nv_bfloat16><<<grid, w * 32, smem, ST(stream)>>>(S, R, L, lds, amax, clip, drop_p, seed,
+    softmax_fwd_kernel<__nv_bfloat16><<<grid, w * 32, smem, ST(stream)>>>(S, R, L, lds, amax, clip, drop_p, seed, (const unsigned long long*)seed_dev,
                                                                           (__nv_bfloat16*)P, ldp, lse, 0, diag);
   }
   SX_CHECK_CUDA(cudaGetLastError());
@@ -796,13 +804,13 @@ extern "C" int sx_softmax_fwd(const float* S, int64_t R, int32_t L, int64_t lds,
 }
 
 extern "C" int sx_softmax_bwd(const float* dP, int64_t ldd, const float* S, int64_t lds, const float* lse, int64_t R,
-                              int32_t L, const float* amax, float clip, float drop_p, uint64_t seed, int64_t ldp_fwd,
+                              int32_t L, const float* amax, float clip, float drop_p, uint64_t seed, const uint64_t* seed_dev, int64_t ldp_fwd,
                               void* dS, int32_t ds_dtype, int64_t ldo, int32_t round_tf32, void* stream) {
   if (ds_dtype == SX_F32 && L % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ldo % 4 == 0 && al16(S) && al16(dP) &&
       al16(dS) && nv_for(L)) {
     const int grid = grid_for_rows(R, FAST_WARPS, sms_cached() * 2);
 #define SX_LAUNCH(NV_)                                                                                             \
-  softmax_bwd_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(dP, ldd, S, lds, lse, R, L, amax, clip, drop_p, seed, \
+  softmax_bwd_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(dP, ldd, S, lds, lse, R, L, amax, clip, drop_p, seed, (const unsigned long long*)seed_dev, \
                                                                   ldp_fwd, (float*)dS, ldo, round_tf32)
     switch (nv_for(L)) { case 2: SX_LAUNCH(2); break; case 4: SX_LAUNCH(4); break; case 8: SX_LAUNCH(8); break;
                          default: SX_LAUNCH(16); }
@@ -816,12 +824,12 @@ extern "C" int sx_softmax_bwd(const float* dP, int64_t ldd, const float* S, int6
   const int grid = grid_for_rows(R, w, sms_cached());
   if (ds_dtype == SX_F32) {
     if (set_smem(softmax_bwd_kernel<float>, smem)) return -2;
-    softmax_bwd_kernel<float><<<grid, w * 32, smem, ST(stream)>>>(dP, ldd, S, lds, lse, R, L, amax, clip, drop_p, seed,
+    softmax_bwd_kernel<float><<<grid, w * 32, smem, ST(stream)>>>(dP, ldd, S, lds, lse, R, L, amax, clip, drop_p, seed, (const unsigned long long*)seed_dev,
                                                                    ldp_fwd, (float*)dS, ldo, round_tf32);
   } else {
     if (set_smem(softmax_bwd_kernel<__nv_bfloat16>, smem)) return -2;
     softmax_bwd_kernel<__nv_bfloat16><<<grid, w * 32, smem, ST(stream)>>>(
-        dP, ldd, S, lds, lse, R, L, amax, clip, drop_p, seed, ldp_fwd, (__nv_bfloat16*)dS, ldo, 0);
+        dP, ldd, S, lds, lse, R, L, amax, clip, drop_p, seed, (const unsigned long long*)seed_dev, ldp_fwd, (__nv_bfloat16*)dS, ldo, 0);
   }
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -881,13 +889,13 @@ extern "C" int sx_layernorm_bwd(const float* dy, const float* x, int64_t R, int3
 }
 
 extern "C" int sx_ln_softaggr_fwd(const float* Y, int32_t B, int32_t M, int32_t N, int32_t F, const float* g,
-                                  const float* b, const float* ws, const float* bs, float drop_p, uint64_t seed,
+                                  const float* b, const float* ws, const float* bs, float drop_p, uint64_t seed, const uint64_t* seed_dev,
                                   float* out, float* stats, float* wts, void* stream) {
   SX_REQUIRE(M >= 1 && M <= MAX_MODES, "sx_ln_softaggr_fwd: num_modes %d not in 1..%d", M, MAX_MODES);
   if (F % 4 == 0 && nv_for(F) && al16(Y) && al16(out) && al16(g) && al16(b) && al16(ws)) {
     const int grid = grid_for_rows((long long)B * N, FAST_WARPS, sms_cached() * 2);
 #define SX_LAUNCH(NV_)                                                                                          \
-  ln_softaggr_fwd_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(Y, B, M, N, F, g, b, ws, bs, drop_p, seed, out, \
+  ln_softaggr_fwd_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(Y, B, M, N, F, g, b, ws, bs, drop_p, seed, (const unsigned long long*)seed_dev, out, \
                                                                       stats, wts)
     switch (nv_for(F)) { case 2: SX_LAUNCH(2); break; case 4: SX_LAUNCH(4); break; case 8: SX_LAUNCH(8); break;
                          default: SX_LAUNCH(16); }
@@ -901,13 +909,13 @@ extern "C" int sx_ln_softaggr_fwd(const float* Y, int32_t B, int32_t M, int32_t 
   const size_t smem = (size_t)ROW_WARPS * M * F * 4;
   if (set_smem(ln_softaggr_fwd_kernel, smem)) return -2;
   ln_softaggr_fwd_kernel<<<grid_for_rows((long long)B * N, ROW_WARPS, sms_cached()), ROW_WARPS * 32, smem, ST(stream)>>>(
-      Y, B, M, N, F, g, b, ws, bs, drop_p, seed, out, stats, wts);
+      Y, B, M, N, F, g, b, ws, bs, drop_p, seed, (const unsigned long long*)seed_dev, out, stats, wts);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int sx_ln_softaggr_bwd(const float* dout, const float* Y, int32_t B, int32_t M, int32_t N, int32_t F,
-                                  const float* g, const float* b, const float* ws, float drop_p, uint64_t seed,
+                                  const float* g, const float* b, const float* ws, float drop_p, uint64_t seed, const uint64_t* seed_dev,
                                   const float* stats, const float* wts, void* dY, int32_t dy_dtype, int32_t round_tf32,
                                   float* dg, float* db, float* dws, float* dbs, float* dscore_scratch, void* stream) {
   SX_REQUIRE(M >= 1 && M <= MAX_MODES, "sx_ln_softaggr_bwd: num_modes %d not in 1..%d", M, MAX_MODES);
@@ -915,7 +923,7 @@ extern "C" int sx_ln_softaggr_bwd(const float* dout, const float* Y, int32_t B, 
       al16(b) && al16(ws)) {
     const int grid = grid_for_rows((long long)B * N, FAST_WARPS, sms_cached() * 2);
 #define SX_LAUNCH(NV_)                                                                                              \
-  ln_softaggr_bwd_rows_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(dout, Y, B, M, N, F, g, b, ws, drop_p, seed, \
+  ln_softaggr_bwd_rows_fast<NV_><<<grid, FAST_WARPS * 32, 0, ST(stream)>>>(dout, Y, B, M, N, F, g, b, ws, drop_p, seed, (const unsigned long long*)seed_dev, \
                                                                            stats, wts, (float*)dY, dscore_scratch, dbs, \
                                                                            round_tf32)
     switch (nv_for(F)) { case 2: SX_LAUNCH(2); break; case 4: SX_LAUNCH(4); break; case 8: SX_LAUNCH(8); break;
@@ -928,7 +936,7 @@ extern "C" int sx_ln_softaggr_bwd(const float* dout, const float* Y, int32_t B, 
     if (gy > cap) gy = cap;
     if (gy < 1) gy = 1;
     dim3 grid2(sx_ceil_div(F, 128), gy), blk(32, 8);
-    ln_softaggr_bwd_cols_fast<<<grid2, blk, 0, ST(stream)>>>(dout, Y, B, M, N, F, g, b, ws, drop_p, seed, stats, wts,
+    ln_softaggr_bwd_cols_fast<<<grid2, blk, 0, ST(stream)>>>(dout, Y, B, M, N, F, g, b, ws, drop_p, seed, (const unsigned long long*)seed_dev, stats, wts,
                                                              dscore_scratch, dg, db, dws);
     SX_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -939,29 +947,30 @@ extern "C" int sx_ln_softaggr_bwd(const float* dout, const float* Y, int32_t B, 
   if (dy_dtype == SX_F32) {
     if (set_smem(ln_softaggr_bwd_kernel<float>, smem)) return -2;
     ln_softaggr_bwd_kernel<float><<<grid, ROW_WARPS * 32, smem, ST(stream)>>>(
-        dout, Y, B, M, N, F, g, b, ws, drop_p, seed, stats, wts, (float*)dY, dg, db, dws, dbs, round_tf32);
+        dout, Y, B, M, N, F, g, b, ws, drop_p, seed, (const unsigned long long*)seed_dev, stats, wts, (float*)dY, dg, db, dws, dbs, round_tf32);
   } else {
     if (set_smem(ln_softaggr_bwd_kernel<__nv_bfloat16>, smem)) return -2;
     ln_softaggr_bwd_kernel<__nv_bfloat16><<<grid, ROW_WARPS * 32, smem, ST(stream)>>>(
-        dout, Y, B, M, N, F, g, b, ws, drop_p, seed, stats, wts, (__nv_bfloat16*)dY, dg, db, dws, dbs, 0);
+        dout, Y, B, M, N, F, g, b, ws, drop_p, seed, (const unsigned long long*)seed_dev, stats, wts, (__nv_bfloat16*)dY, dg, db, dws, dbs, 0);
   }
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int sx_gelu_bwd(const float* dG, const void* H, int32_t h_dtype, int64_t n, float drop_p, uint64_t seed,
+extern "C" int sx_gelu_bwd(const float* dG, const void* H, int32_t h_dtype, int64_t n, float drop_p, uint64_t seed, const uint64_t* seed_dev,
                            void* dH, int32_t dh_dtype, int32_t round_tf32, void* stream) {
   const int grid = grid_for_rows(n, 256 * 8, sms_cached());
   SX_REQUIRE(h_dtype == dh_dtype, "sx_gelu_bwd: H and dH dtypes must match");
   if (h_dtype == SX_F32 && n % 4 == 0 && al16(dG) && al16(H) && al16(dH))
     gelu_bwd_f4_kernel<<<grid_for_rows(n / 4, 256 * 4, sms_cached()), 256, 0, ST(stream)>>>(
-        (const float4*)dG, (const float4*)H, n / 4, drop_p, seed, (float4*)dH, round_tf32);
+        (const float4*)dG, (const float4*)H, n / 4, drop_p, seed, (const unsigned long long*)seed_dev, (float4*)dH, round_tf32);
   else if (h_dtype == SX_F32)
-    gelu_bwd_kernel<float, float><<<grid, 256, 0, ST(stream)>>>(dG, (const float*)H, n, drop_p, seed, (float*)dH,
+    gelu_bwd_kernel<float, float><<<grid, 256, 0, ST(stream)>>>(dG, (const float*)H, n, drop_p, seed, (const unsigned long long*)seed_dev, (float*)dH,
                                                                  round_tf32);
   else
     gelu_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, ST(stream)>>>(dG, (const __nv_bfloat16*)H, n, drop_p,
-                                                                                seed, (__nv_bfloat16*)dH, 0);
+                                                                                seed, (const unsigned long long*)seed_dev,
+                                                                                (__nv_bfloat16*)dH, 0);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1029,6 +1038,25 @@ extern "C" int sx_colsum_batched(const float* X, int32_t Z1, int64_t stride_z1, 
   if (gy < 1) gy = 1;
   dim3 grid(sx_ceil_div(C, 32), gy, Z0), blk(32, 8);
   colsum_batched_kernel<<<grid, blk, 0, ST(stream)>>>(X, Z1, stride_z1, stride_z0, R, C, ld, out);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+namespace {
+__global__ void seed_derive_kernel(const unsigned long long* base, unsigned long long add, unsigned long long* out) {
+  out[0] = (base ? base[0] : 0ull) + add;
+}
+__global__ void seed_advance_kernel(unsigned long long* base, unsigned long long inc) { base[0] += inc; }
+}  // namespace
+
+extern "C" int sx_seed_derive(const uint64_t* base, uint64_t add, uint64_t* out, void* stream) {
+  seed_derive_kernel<<<1, 1, 0, ST(stream)>>>((const unsigned long long*)base, add, (unsigned long long*)out);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_seed_advance(uint64_t* base, uint64_t inc, void* stream) {
+  seed_advance_kernel<<<1, 1, 0, ST(stream)>>>((unsigned long long*)base, inc);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

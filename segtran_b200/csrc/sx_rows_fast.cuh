@@ -61,8 +61,9 @@ template <int NV>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 ln_softaggr_fwd_fast(const float* __restrict__ Y, int B, int M, int N, int F, const float* __restrict__ g,
                      const float* __restrict__ b, const float* __restrict__ ws, const float* __restrict__ bs,
-                     float drop_p, unsigned long long seed, float* __restrict__ out, float* __restrict__ stats,
+                     float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev, float* __restrict__ out, float* __restrict__ stats,
                      float* __restrict__ wts) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const long long T_ = (long long)B * N;
@@ -140,9 +141,10 @@ template <int NV>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 ln_softaggr_bwd_rows_fast(const float* __restrict__ dout, const float* __restrict__ Y, int B, int M, int N, int F,
                           const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ ws,
-                          float drop_p, unsigned long long seed, const float* __restrict__ stats,
+                          float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev, const float* __restrict__ stats,
                           const float* __restrict__ wts, float* __restrict__ dY, float* __restrict__ dscore_out,
                           float* __restrict__ dbs, int rnd) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const long long T_ = (long long)B * N;
@@ -224,9 +226,10 @@ ln_softaggr_bwd_rows_fast(const float* __restrict__ dout, const float* __restric
 __global__ void __launch_bounds__(256)
 ln_softaggr_bwd_cols_fast(const float* __restrict__ dout, const float* __restrict__ Y, int B, int M, int N, int F,
                           const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ ws,
-                          float drop_p, unsigned long long seed, const float* __restrict__ stats,
+                          float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev, const float* __restrict__ stats,
                           const float* __restrict__ wts, const float* __restrict__ dscore_in, float* __restrict__ dg,
                           float* __restrict__ db, float* __restrict__ dws) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, aw = ag;
@@ -267,8 +270,9 @@ ln_softaggr_bwd_cols_fast(const float* __restrict__ dout, const float* __restric
 template <int NV>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 softmax_fwd_fast(const float* __restrict__ S, long long R, int L, long long lds, const float* __restrict__ amax,
-                 float clip, float drop_p, unsigned long long seed, float* __restrict__ P, long long ldp,
+                 float clip, float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev, float* __restrict__ P, long long ldp,
                  float* __restrict__ lse, int rnd, float* __restrict__ diag) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool do_clip = amax && (*amax > clip);
   if (diag && amax && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -316,8 +320,9 @@ template <int NV>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 softmax_bwd_fast(const float* __restrict__ dP, long long ldd, const float* __restrict__ S, long long lds,
                  const float* __restrict__ lse, long long R, int L, const float* __restrict__ amax, float clip,
-                 float drop_p, unsigned long long seed, long long ldp_fwd, float* __restrict__ dS, long long ldo,
+                 float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev, long long ldp_fwd, float* __restrict__ dS, long long ldo,
                  int rnd) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool do_clip = amax && (*amax > clip);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -382,8 +387,9 @@ __global__ void __launch_bounds__(FAST_WARPS * 32)
 prologue_bwd_rows_fast(const float* __restrict__ dh, const float* __restrict__ x, long long R, int N, int C,
                        const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ pe, int C0,
                        long long pe_bstride, float posw, const float* __restrict__ mask, float drop_p,
-                       unsigned long long seed, const float* __restrict__ stats, float* __restrict__ dx,
+                       unsigned long long seed, const unsigned long long* __restrict__ seed_dev, const float* __restrict__ stats, float* __restrict__ dx,
                        float* __restrict__ dt_out) {
+  seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   for (long long r = (long long)blockIdx.x * FAST_WARPS + warp; r < R; r += (long long)gridDim.x * FAST_WARPS) {

@@ -198,13 +198,14 @@ static void perf(int op, int amaj, int bmaj, int M, int N, int K, int Z) {
 }
 
 int main(int argc, char** argv) {
-  bool do_perf = false;
+  bool do_perf = false, ksweep = false;
   std::string only;
   for (int i = 1; i < argc; ++i) {
     char* eq = strchr(argv[i], '=');
     if (!eq) continue;
     std::string k(argv[i], eq - argv[i]);
     if (k == "perf") { do_perf = atoi(eq + 1) != 0; continue; }
+    if (k == "ksweep") { ksweep = atoi(eq + 1) != 0; continue; }
     if (k == "only") { only = eq + 1; continue; }
     if (sx_gemm_debug_set(k.c_str(), atoll(eq + 1)) != 0) { printf("bad knob %s\n", k.c_str()); return 3; }
     printf("knob %s=%lld\n", k.c_str(), atoll(eq + 1));
@@ -252,6 +253,12 @@ int main(int argc, char** argv) {
     if (r == 2) { printf("aborting after launch failure (context likely poisoned)\n"); break; }
   }
   printf("SUMMARY %d/%d cases passed\n", ran - fails, ran);
+  if (ksweep) {
+    const int Ks[] = {128, 256, 512, 1024, 2048, 4096};
+    for (int kk : Ks) perf(T, K_, K_, 128 * 74, 256 * 20, kk, 1);      // 1480 tiles = exactly 10 waves of 148
+    for (int kk : Ks) perf(H, K_, K_, 128 * 74, 256 * 20, kk, 1);
+    return 0;
+  }
   if (do_perf) {
     perf(H, K_, K_, 8192, 8192, 8192, 1);
     perf(T, K_, K_, 8192, 8192, 8192, 1);

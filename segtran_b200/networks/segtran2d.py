@@ -208,9 +208,12 @@ class Segtran2d(SegtranInitWeights):
         if not self.scales_printed:
             print("\nImage scales: %dx%d. Feat: %s. Voxels: %s" % (sH, sW, list(grid), list(vfeat.shape)))
             self.scales_printed = True
-        idx = gen_all_indices(grid, device=vfeat.device).view(-1, 2).float() * \
-            torch.tensor([[float(sH), float(sW)]], device=vfeat.device)
-        voxels_pos = idx.unsqueeze(0).expand(B0, -1, -1)
+        key = (tuple(grid), sH, sW, str(vfeat.device))
+        if getattr(self, "_pos_cache_key", None) != key:             # built once per shape: no H2D copy per step
+            idx = gen_all_indices(grid, device=vfeat.device).view(-1, 2).float() * \
+                torch.tensor([[float(sH), float(sW)]], device=vfeat.device)
+            self._pos_cache_key, self._pos_cache = key, idx
+        voxels_pos = self._pos_cache.unsqueeze(0).expand(B0, -1, -1)
         fused = self.voxel_fusion(vfeat, voxels_pos, None if vmask is None else vmask.unsqueeze(2), grid)
         self.layers_attn_scores = self.voxel_fusion.layers_attn_scores
         for i in range(self.num_translayers):

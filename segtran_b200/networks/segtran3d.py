@@ -240,8 +240,12 @@ class Segtran3d(SegtranInitWeights):
             print("\nFeat: %s, Voxels: %s. Model DHW scales: %dx%dx%d. Total scales: %s" %
                   (list(grid), list(vfeat.shape), sD, sH, sW, scale))
             self.scales_printed = True
-        idx = gen_all_indices(grid, device=vfeat.device).view(-1, 3).float() * torch.tensor([scale], device=vfeat.device)
-        voxels_pos = idx.unsqueeze(0).expand(B, -1, -1)               # one set of positions, shared by the batch
+        key = (tuple(grid), tuple(scale), str(vfeat.device))
+        if getattr(self, "_pos_cache_key", None) != key:             # built once per shape: no H2D copy per step
+            idx = gen_all_indices(grid, device=vfeat.device).view(-1, 3).float() * \
+                torch.tensor([scale], device=vfeat.device)
+            self._pos_cache_key, self._pos_cache = key, idx
+        voxels_pos = self._pos_cache.unsqueeze(0).expand(B, -1, -1)  # one set of positions, shared by the batch
         fused = self.voxel_fusion(vfeat, voxels_pos, None if vmask is None else vmask.unsqueeze(2), grid)
         self.layers_attn_scores = self.voxel_fusion.layers_attn_scores
         self.orig_feat_shape = grid

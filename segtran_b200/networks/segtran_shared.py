@@ -39,9 +39,6 @@ def gen_all_indices(shape, device):
     return torch.stack(torch.meshgrid(*axes, indexing='ij'), dim=len(axes))
 
 
-def _seed_from_torch() -> int:
-    """Dropout seed drawn from torch's (seedable) CPU generator: masks are reproducible under manual_seed."""
-    return int(torch.randint(0, 2 ** 62, (1,)).item())
 
 
 class SegtranConfig:
@@ -131,7 +128,7 @@ class MMSharedMid(nn.Module):
     def forward(self, x):                       # x [B,M,U,F]
         p = self.dropout.p if self.training else 0.0
         return ops.linear(x, self.shared_linear.weight, self.shared_linear.bias, gelu=True, drop_p=p,
-                          seed=_seed_from_torch() if p > 0 else 0)
+                          seed=ops.new_dropout_seed(x.device) if p > 0 else 0)
 
 
 class MMPrivateMid(nn.Module):
@@ -232,7 +229,7 @@ class ExpandedFeatTrans(nn.Module):
         ln = self.output.resout_norm_layer
         f2s = self.feat_softaggr.feat2score
         return ops.ln_softaggr(y, ln.weight, ln.bias, f2s.weight, f2s.bias, drop_p=p,
-                               seed=_seed_from_torch() if p > 0 else 0)
+                               seed=ops.new_dropout_seed(y.device) if p > 0 else 0)
 
 
 class CrossAttFeatTrans(nn.Module):
@@ -311,7 +308,7 @@ class CrossAttFeatTrans(nn.Module):
         amax = torch.full((1,), -3.0e38, device=dev)
         s = ops.attn_scores(q, k, M, amax)                                   # [B,M,U1,U2], max tracked on device
         p = self.att_dropout.p if self.training else 0.0
-        probs = ops.softmax(s, amax, float(self.attn_clip), p, _seed_from_torch() if p > 0 else 0, self._diag)
+        probs = ops.softmax(s, amax, float(self.attn_clip), p, ops.new_dropout_seed(dev) if p > 0 else 0, self._diag)
         self.attention_scores = s if self.keep_attn_scores else None
         if self.training:
             self.call_count += 1
@@ -450,12 +447,14 @@ class SegtranFusionEncoder(nn.Module):
         B, N, _ = vfeat.shape
         mask = vmask.reshape(B * N).to(torch.float32).contiguous() if vmask is not None else None
         x = vfeat if vfeat.dtype == torch.float32 else vfeat.float()
+        if self.training and x.is_cuda:
+            ops.advance_seed(x.device)           # one new dropout stream per training step (device side, graph safe)
         for i, layer in enumerate(self.translayers):
             pe = self.pos_code_layer(orig_feat_shape, voxels_pos)
             ln = self.vfeat_norm_layers[i]
             p = self.dropout.p if (self.training and i == 0) else 0.0
             h = ops.prologue(x, ln.weight, ln.bias, pe, float(self.pos_code_weight), mask, p,
-                             _seed_from_torch() if p > 0 else 0)
+                             ops.new_dropout_seed(x.device) if p > 0 else 0)
             x = layer(h, pos_biases=None)
             self.layers_vfeat.append(x)
             if self.use_attn_consist_loss:

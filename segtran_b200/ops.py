@@ -33,6 +33,53 @@ def get_precision() -> str:
     return _PRECISION
 
 
+# ------------------------------------------------------------------------------------------------
+# dropout seeds (CUDA-graph safe): a per-device base seed lives on the GPU; every dropout site derives its own
+# per-call device seed from it in stream order and keeps that tensor for backward, so a captured graph draws a
+# fresh mask on every replay and fwd/bwd of one call always agree.
+# ------------------------------------------------------------------------------------------------
+_MASK64 = (1 << 64) - 1
+_base_seeds = {}
+_site_counter = [0]
+
+
+def _base_seed(device) -> torch.Tensor:
+    key = (device.type, device.index)
+    t = _base_seeds.get(key)
+    if t is None:
+        t = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(device)       # follows torch.manual_seed
+        _base_seeds[key] = t
+    return t
+
+
+def reseed(seed: int, device=None):
+    """Set the dropout base seed explicitly (all devices, or one)."""
+    for key, t in list(_base_seeds.items()):
+        if device is None or (device.type, device.index) == key:
+            t.fill_(int(seed) & ((1 << 62) - 1))
+
+
+def advance_seed(device):
+    """Bump the base seed once per training step (captured into CUDA graphs like any other kernel)."""
+    L.call("sx_seed_advance", _base_seed(device).data_ptr(), 0xD1B54A32D192ED03, _stream())
+
+
+def new_dropout_seed(device) -> torch.Tensor:
+    """Per-call device seed = base seed + a unique site constant; pass it as `seed=` to a dropout-capable op."""
+    _site_counter[0] += 1
+    t = torch.empty(1, device=device, dtype=torch.int64)
+    L.call("sx_seed_derive", _base_seed(device).data_ptr(), (_site_counter[0] * 0x9E3779B97F4A7C15) & _MASK64,
+           t.data_ptr(), _stream())
+    return t
+
+
+def _seed_args(seed):
+    """seed: python int (by value) or int64 device tensor (by pointer) -> (value, pointer)."""
+    if isinstance(seed, torch.Tensor):
+        return 0, seed.data_ptr()
+    return int(seed) & _MASK64, None
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -146,7 +193,7 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = N
     if amax is not None:
         g.amax = amax.data_ptr()
     g.drop_p = drop_p
-    g.drop_seed = seed
+    g.drop_seed, g.drop_seed_dev = _seed_args(seed)
     L.call("sx_gemm", C.byref(g), _stream())
     return out
 
@@ -227,7 +274,7 @@ class _Linear(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
         if gelu:
             dh = torch.empty_like(dy2)
-            L.call("sx_gelu_bwd", dy2.data_ptr(), h.data_ptr(), L.SX_F32, dy2.numel(), drop_p, seed, dh.data_ptr(),
+            L.call("sx_gelu_bwd", dy2.data_ptr(), h.data_ptr(), L.SX_F32, dy2.numel(), drop_p, *_seed_args(seed), dh.data_ptr(),
                    L.SX_F32, 1, _stream())
             dy2 = dh
         dx = dW = db = None
@@ -293,7 +340,7 @@ class _Softmax(torch.autograd.Function):
         R = S.numel() // Lr
         P = _rowpad_empty(S.shape, S.device)
         lse = torch.empty(R, device=S.device, dtype=torch.float32)
-        L.call("sx_softmax_fwd", S.data_ptr(), R, Lr, ld, _ptr(amax), clip, drop_p, seed, P.data_ptr(), L.SX_F32,
+        L.call("sx_softmax_fwd", S.data_ptr(), R, Lr, ld, _ptr(amax), clip, drop_p, *_seed_args(seed), P.data_ptr(), L.SX_F32,
                P.stride(-2), 1, lse.data_ptr(), _ptr(diag), _stream())
         ctx.save_for_backward(S, lse, amax)
         ctx.meta = (clip, drop_p, seed, P.stride(-2))
@@ -308,7 +355,7 @@ class _Softmax(torch.autograd.Function):
         R = S.numel() // Lr
         dS = _rowpad_empty(S.shape, S.device)
         L.call("sx_softmax_bwd", dP.data_ptr(), dP.stride(-2), S.data_ptr(), S.stride(-2), lse.data_ptr(), R, Lr,
-               _ptr(amax), clip, drop_p, seed, ldp, dS.data_ptr(), L.SX_F32, dS.stride(-2), 1, _stream())
+               _ptr(amax), clip, drop_p, *_seed_args(seed), ldp, dS.data_ptr(), L.SX_F32, dS.stride(-2), 1, _stream())
         return dS, None, None, None, None, None
 
 
@@ -417,7 +464,7 @@ class _LnSoftAggr(torch.autograd.Function):
         stats = torch.empty((B, M, N, 2), device=Y.device, dtype=torch.float32)
         wts = torch.empty((B, M, N), device=Y.device, dtype=torch.float32)
         L.call("sx_ln_softaggr_fwd", Y.data_ptr(), B, M, N, Fd, g.data_ptr(), b.data_ptr(), ws.data_ptr(),
-               bs.data_ptr(), drop_p, seed, out.data_ptr(), stats.data_ptr(), wts.data_ptr(), _stream())
+               bs.data_ptr(), drop_p, *_seed_args(seed), out.data_ptr(), stats.data_ptr(), wts.data_ptr(), _stream())
         ctx.save_for_backward(Y, g, b, ws, stats, wts)
         ctx.meta = (drop_p, seed, bs.shape, ws.shape)
         return out
@@ -435,7 +482,7 @@ class _LnSoftAggr(torch.autograd.Function):
         dbs = torch.zeros(1, device=Y.device, dtype=torch.float32)
         scratch = torch.empty(B * M * N, device=Y.device, dtype=torch.float32)
         L.call("sx_ln_softaggr_bwd", dout.data_ptr(), Y.data_ptr(), B, M, N, Fd, g.data_ptr(), b.data_ptr(),
-               ws.data_ptr(), drop_p, seed, stats.data_ptr(), wts.data_ptr(), dY.data_ptr(), L.SX_F32, 1, dg.data_ptr(),
+               ws.data_ptr(), drop_p, *_seed_args(seed), stats.data_ptr(), wts.data_ptr(), dY.data_ptr(), L.SX_F32, 1, dg.data_ptr(),
                db.data_ptr(), dws.data_ptr(), dbs.data_ptr(), scratch.data_ptr(), _stream())
         return dY, dg, db, dws.view(ws_shape), dbs.view(bs_shape), None, None
 
@@ -484,7 +531,7 @@ class _Prologue(torch.autograd.Function):
         h = torch.empty_like(x)
         stats = torch.empty((B * N, 4), device=x.device, dtype=torch.float32)
         L.call("sx_prologue_fwd", x.data_ptr(), B, N, Cd, g.data_ptr(), b.data_ptr(), pe.data_ptr(), C0, pe_bstride,
-               posw, _ptr(mask), drop_p, seed, h.data_ptr(), L.SX_F32, 1, stats.data_ptr(), _stream())
+               posw, _ptr(mask), drop_p, *_seed_args(seed), h.data_ptr(), L.SX_F32, 1, stats.data_ptr(), _stream())
         ctx.save_for_backward(x, g, b, pe, mask, stats)
         ctx.meta = (posw, drop_p, seed, pe_bstride)
         return h
@@ -502,7 +549,7 @@ class _Prologue(torch.autograd.Function):
         dpe = torch.zeros_like(pe) if ctx.needs_input_grad[3] else None
         scratch = torch.empty_like(x)
         L.call("sx_prologue_bwd", dh.data_ptr(), x.data_ptr(), B, N, Cd, g.data_ptr(), b.data_ptr(), pe.data_ptr(), C0,
-               pe_bstride, posw, _ptr(mask), drop_p, seed, stats.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(),
+               pe_bstride, posw, _ptr(mask), drop_p, *_seed_args(seed), stats.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(),
                _ptr(dpe), scratch.data_ptr(), _stream())
         return dx, dg, db, dpe, None, None, None, None
 

@@ -18,7 +18,7 @@ import torch.distributed as dist
 
 
 class GradBucket:
-    def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None, overlap_chunks: int = 0):
         seen, self.params = set(), []
         for p in params:                      # tied parameters (query/key) appear once
             if p.requires_grad and id(p) not in seen:
@@ -37,11 +37,53 @@ class GradBucket:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self._comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        # NCCL averages inside the collective (no extra pass over the bucket); gloo has no AVG -> SUM then scale
+        self._avg = self.world > 1 and dist.get_backend(process_group) == "nccl"
+        self._op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         self._work = None
+        self._works: List = []
+        # optional overlap of the exchange with the rest of backward: the bucket is cut into contiguous chunks and a
+        # chunk's all-reduce is issued (on the side stream) as soon as autograd has produced all of its gradients
+        self._chunks = []
+        if overlap_chunks > 1 and self.world > 1:
+            target = (self.numel + overlap_chunks - 1) // overlap_chunks
+            off, start, members = 0, 0, []
+            for p in self.params:
+                members.append(p)
+                off += p.numel()
+                if off - start >= target:
+                    self._chunks.append({"lo": start, "hi": off, "n": len(members), "left": len(members), "sent": False})
+                    for q in members:
+                        q._sx_chunk = len(self._chunks) - 1
+                    start, members = off, []
+            if members:
+                self._chunks.append({"lo": start, "hi": off, "n": len(members), "left": len(members), "sent": False})
+                for q in members:
+                    q._sx_chunk = len(self._chunks) - 1
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._on_grad_ready)
+
+    def _send_chunk(self, c):
+        c["sent"] = True
+        view = self.flat[c["lo"]:c["hi"]]
+        if self._comm is not None:
+            self._comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm):
+                self._works.append(dist.all_reduce(view, op=self._op, group=self.group, async_op=True))
+        else:
+            self._works.append(dist.all_reduce(view, op=self._op, group=self.group, async_op=True))
+
+    def _on_grad_ready(self, p):
+        c = self._chunks[p._sx_chunk]
+        c["left"] -= 1
+        if c["left"] == 0 and not c["sent"]:
+            self._send_chunk(c)
 
     def zero(self):
         """Replaces optimizer.zero_grad(): one memset instead of one per parameter; .grad views stay attached."""
         self.flat.zero_()
+        for c in self._chunks:
+            c["left"], c["sent"] = c["n"], False
 
     def reattach(self):
         """Call if something replaced p.grad (e.g. zero_grad(set_to_none=True))."""
@@ -56,28 +98,52 @@ class GradBucket:
         """Average the bucket over ranks; returns immediately (the transfer runs on a side stream on GPUs)."""
         if self.world == 1:
             return
+        if self._chunks:                      # overlap mode: send whatever backward has not triggered (unused params)
+            for c in self._chunks:
+                if not c["sent"]:
+                    self._send_chunk(c)
+            return
         if self._comm is not None:
             self._comm.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._comm):
-                self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self._work = dist.all_reduce(self.flat, op=self._op, group=self.group, async_op=True)
                 self._scaled = False
         else:
-            self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._work = dist.all_reduce(self.flat, op=self._op, group=self.group, async_op=True)
             self._scaled = False
 
     def wait(self):
         """Make the averaged gradients visible to the current stream (call before the optimizer step)."""
-        if self.world == 1 or self._work is None:
+        if self.world == 1:
+            return
+        if self._chunks:
+            if self._comm is not None:
+                with torch.cuda.stream(self._comm):
+                    for w in self._works:
+                        w.wait()
+                    self._scale()
+                torch.cuda.current_stream().wait_stream(self._comm)
+            else:
+                for w in self._works:
+                    w.wait()
+                self._scale()
+            self._works = []
+            return
+        if self._work is None:
             return
         if self._comm is not None:
             with torch.cuda.stream(self._comm):
                 self._work.wait()
-                self.flat.mul_(1.0 / self.world)
+                self._scale()
             torch.cuda.current_stream().wait_stream(self._comm)
         else:
             self._work.wait()
-            self.flat.mul_(1.0 / self.world)
+            self._scale()
         self._work = None
+
+    def _scale(self):
+        if not self._avg:
+            self.flat.mul_(1.0 / self.world)
 
     def bytes(self) -> int:
         return self.numel * self.flat.element_size()

@@ -59,3 +59,48 @@ def test_clamp_case_matches_reference():
     assert t.ator_out_trans.clamp_count == 1 and t.in_ator_trans.clamp_count == 0
     assert abs(t.ator_out_trans.max_attn - fx["max_attn"][1]) < 1e-2 * fx["max_attn"][1]
     assert rel_err(y, fx["out"]) < 5e-2
+
+
+def test_training_mode_dropout_runs_and_is_consistent():
+    """Dropout on (reference default 0.2): finite outputs/gradients, masks change from step to step (device-side
+    seed advance), and the whole step replays under a CUDA graph with a fresh mask per replay."""
+    from segtran_b200 import ops
+    from segtran_b200.graph import CapturedStep
+    fx = load_golden("enc3d_small")
+    enc = build_b200_encoder(fx, dropout=0.2).train()
+    x = fx["x"].cuda().requires_grad_()
+    pos, mask, grid = fx["voxels_pos"].cuda(), fx["vmask"].cuda(), torch.Size(fx["grid"])
+    y1 = enc(x, pos, mask, grid)
+    y2 = enc(x, pos, mask, grid)
+    assert torch.isfinite(y1).all() and not torch.equal(y1, y2)
+    y1.square().mean().backward()
+    assert torch.isfinite(x.grad).all()
+    # expectation over masks stays close to the no-dropout output (inverted dropout keeps the mean)
+    enc.eval()
+    with torch.no_grad():
+        y0 = enc(x, pos, mask, grid)
+    enc.train()
+    acc = torch.zeros_like(y0)
+    with torch.no_grad():
+        for _ in range(64):
+            acc += enc(x, pos, mask, grid)
+    assert rel_err(acc / 64, y0) < 0.25
+
+    # graph capture: fresh module and input that have never been used on the (legacy) default stream — autograd binds
+    # a leaf's gradient accumulation to the stream of its first use, and that must not be the legacy stream
+    enc2 = build_b200_encoder(fx, dropout=0.2).train()
+    x2 = fx["x"].cuda().requires_grad_()
+
+    def step():
+        x2.grad = None
+        for p_ in enc2.parameters():
+            p_.grad = None
+        out = enc2(x2, pos, mask, grid)
+        out.square().mean().backward()
+        return out
+
+    g = CapturedStep(step, warmup=2)
+    a = g().clone()
+    b = g().clone()
+    assert torch.isfinite(a).all() and not torch.equal(a, b)       # new mask on every replay
+    assert g.kernel_launches > 20

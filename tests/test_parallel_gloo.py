@@ -16,14 +16,14 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, overlap=0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from segtran_b200.parallel import GradBucket
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.GELU(), torch.nn.Linear(5, 3))
     net[2].weight = net[2].weight                      # plain module; tying handled by id() de-duplication
-    bucket = GradBucket(net.parameters())
+    bucket = GradBucket(net.parameters(), overlap_chunks=overlap)
     x = torch.arange(4 * 6, dtype=torch.float32).view(4, 6) / 10.0
     xs = x[rank * 2:(rank + 1) * 2]                    # batch-split data parallelism (train3d.py:495)
     for it in range(2):                                # second iteration checks that .grad views stay attached
@@ -43,11 +43,15 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_grad_bucket_two_ranks_gloo():
+import pytest
+
+
+@pytest.mark.parametrize("overlap", [0, 3])
+def test_grad_bucket_two_ranks_gloo(overlap):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q, overlap)) for r in range(world)]
     for p in ps:
         p.start()
     res = [q.get(timeout=120) for _ in ps]
