@@ -346,10 +346,43 @@ class SqueezedAttFeatTrans(nn.Module):
         self.attractors = nn.Parameter(torch.randn(1, self.num_attractors, self.in_feat_dim))
         self.attention_scores = None
 
+    def _in_squeeze_reassociated(self, in_feat):
+        """In-squeeze (reference :813 -> CrossAttFeatTrans.forward with M=1, no FFN) with the two token-sized
+        projections re-associated away: with Q1 = Att Wq^T + bq,
+            S1 = Q1 (h Wk^T + bk)^T / sqrt(C) = ((Q1 Wk) h^T + (Q1 . bk) 1^T) / sqrt(C)
+            Z  = P1 (h Wv^T)                  = (P1 h) Wv^T
+        so the [N x C x C] key and value GEMMs become [A x C x C] ones; exact up to fp rounding."""
+        t = self.in_ator_trans
+        C = self.in_feat_dim
+        q1 = ops.linear(self.attractors, t.query.weight, t.query.bias)               # [1,A,C]
+        qw = ops.linear(q1, t.key.weight.t())                                         # Q1 Wk            [1,A,C]
+        rb = None
+        if t.key.bias is not None:                                                    # (Q1 . bk) / sqrt(C)  [A]
+            rb = ops.scale(ops.matvec(q1[0], t.key.bias), 1.0 / math.sqrt(C))
+        dev = in_feat.device
+        if t._diag is None or t._diag.device != dev:
+            t._diag = torch.tensor([-3.0e38, 0.0], device=dev)
+        amax = torch.full((1,), -3.0e38, device=dev)
+        s = ops.attn_scores(qw, in_feat, 1, amax, rb)                                  # [B,1,A,N]
+        p = t.att_dropout.p if t.training else 0.0
+        probs = ops.softmax(s, amax, float(t.attn_clip), p, ops.new_dropout_seed(dev) if p > 0 else 0, t._diag)
+        t.attention_scores = s if t.keep_attn_scores else None
+        if t.training:
+            t.call_count += 1
+        u = ops.attn_pv(probs, in_feat, 1)                                             # P1 h            [B,1,A,C]
+        ot = t.out_trans
+        z = ops.linear(u[:, 0], ot.first_linear.weight)                                # (P1 h) Wv^T     [B,A,C]
+        return ops.layer_norm(z, ot.first_norm_layer.weight, ot.first_norm_layer.bias)
+
     def forward(self, in_feat, pos_biases=None):
         if pos_biases is not None:
             _unsupported("positional biases with squeezed attention")
-        att = self.in_ator_trans(self.attractors, in_feat)          # attractors are batch-invariant: projected once
+        t = self.in_ator_trans
+        if t.num_modes == 1 and not t.out_trans.has_FFN and t.out_trans.first_linear.bias is None \
+                and t.feat_dim == self.in_feat_dim:
+            att = self._in_squeeze_reassociated(in_feat)
+        else:
+            att = t(self.attractors, in_feat)       # attractors are batch-invariant: projected once
         out = self.ator_out_trans(in_feat, att)
         self.attention_scores = self.ator_out_trans.attention_scores
         return out

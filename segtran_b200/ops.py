@@ -126,12 +126,20 @@ def _as4(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def _pick_split_k(M, N, K, Z, bk=32, sms=148):
+def _pick_split_k(M, N, K, Z, bk=32, sms=148, epi=10):
+    """Split-K factor for a GEMM whose tile count does not fill the machine: minimise
+    rounds(tiles*sk / SMs) * (k-blocks per unit + epilogue cost in k-block units)."""
     tiles = ((M + 127) // 128) * ((N + 255) // 256) * Z
     nkb = (K + bk - 1) // bk
-    if tiles >= sms or nkb < 16:
+    if tiles >= 2 * sms or nkb < 16:
         return 1
-    return max(1, min((sms + tiles - 1) // tiles, nkb // 8))
+    best, best_cost = 1, None
+    for sk in range(1, max(1, nkb // 8) + 1):
+        rounds = (tiles * sk + sms - 1) // sms
+        cost = rounds * ((nkb + sk - 1) // sk + epi * (1 if sk == 1 else 2))     # atomics make split epilogues dearer
+        if best_cost is None or cost < best_cost:
+            best, best_cost = sk, cost
+    return best
 
 
 def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, alpha: float = 1.0,
@@ -292,11 +300,13 @@ def linear(x, W, b=None, gelu=False, drop_p=0.0, seed=0):
 
 
 class _AttnScores(torch.autograd.Function):
-    """S[b,m] = scale * Q[b,:,m] K[b,:,m]^T   (segtran_shared.py:566-567); also tracks max(S) on the device.
-    q may have batch 1 (the batch-invariant attractor queries): it is broadcast, and its gradient reduced over b."""
+    """S[b,m] = scale * Q[b,:,m] K[b,:,m]^T (+ row_bias[u1])   (segtran_shared.py:566-567); tracks max(S) on the device.
+    q may have batch 1 (the batch-invariant attractor queries): it is broadcast, and its gradient reduced over b.
+    row_bias [U1] (single-mode only) is the per-query constant of the re-associated in-squeeze (see
+    SqueezedAttFeatTrans): it is added after the scaling, so it must already be scaled."""
 
     @staticmethod
-    def forward(ctx, q, k, M, amax):
+    def forward(ctx, q, k, M, amax, row_bias):
         Bq, U1, Cq = q.shape
         B, U2 = k.shape[0], k.shape[1]
         d = Cq // M
@@ -304,19 +314,22 @@ class _AttnScores(torch.autograd.Function):
         qv = q.view(Bq, U1, M, d).permute(0, 2, 1, 3)         # [Bq,M,U1,d] strided view, d contiguous
         kv = k.view(B, U2, M, d).permute(0, 2, 1, 3)
         S = _rowpad_empty((B, M, U1, U2), q.device)
-        gemm_nt(qv, kv, out=S, alpha=scale, amax=amax, round_out=False)
+        if row_bias is not None and M != 1:
+            raise L.SxError("attn_scores: row_bias needs a single mode")
+        rb = row_bias.contiguous().view(-1) if row_bias is not None else None
+        gemm_nt(qv, kv, out=S, alpha=scale, amax=amax, round_out=False, bias=rb, bias_mode=L.SX_BIAS_M)
         ctx.save_for_backward(q, k)
-        ctx.meta = (M, d, scale)
+        ctx.meta = (M, d, scale, row_bias.shape if row_bias is not None else None)
         return S
 
     @staticmethod
     def backward(ctx, dS):
         q, k = ctx.saved_tensors
-        M, d, scale = ctx.meta
+        M, d, scale, rb_shape = ctx.meta
         Bq, U1, Cq = q.shape
         B, U2 = k.shape[0], k.shape[1]
         dS = _rowpad(dS)
-        dq = dk = None
+        dq = dk = drb = None
         if ctx.needs_input_grad[0]:
             # dQ[b,m] (U1 x d) = scale * dS[b,m] (U1 x U2) . K[b,m] (U2 x d)
             bcast = Bq == 1 and B > 1
@@ -327,7 +340,57 @@ class _AttnScores(torch.autograd.Function):
             dk = torch.empty_like(k)
             gemm_nt(dS.transpose(-1, -2), q.view(Bq, U1, M, d).permute(0, 2, 3, 1),
                     out=dk.view(B, U2, M, d).permute(0, 2, 1, 3), alpha=scale, round_out=False)
-        return dq, dk, None, None
+        if rb_shape is not None and ctx.needs_input_grad[4]:
+            drb = torch.zeros(U1, device=q.device, dtype=torch.float32)     # sum over batch and keys
+            L.call("sx_rowsum", dS.data_ptr(), B * U1, U2, dS.stride(-2), U1, drb.data_ptr(), _stream())
+            drb = drb.view(rb_shape)
+        return dq, dk, None, None, drb
+
+
+class _Scale(torch.autograd.Function):
+    """y = alpha * x (sx_scale kernel)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        L.call("sx_scale", x.data_ptr(), x.numel(), None, alpha, y.data_ptr(), _stream())
+        ctx.alpha = alpha
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _Scale.apply(dy, ctx.alpha), None
+
+
+def scale(x, alpha):
+    return _Scale.apply(x, float(alpha))
+
+
+class _MatVec(torch.autograd.Function):
+    """y[r] = sum_c x[r,c] v[c] on CUDA cores (exact fp32; a K=1 / N=1 product has no business on tensor cores)."""
+
+    @staticmethod
+    def forward(ctx, x, v):
+        x = x.contiguous()
+        v = v.contiguous()
+        R, Cd = x.shape
+        y = _sgemm(x, v, R, 1, Cd, (Cd, 1), (1, 1))[0].view(R)
+        ctx.save_for_backward(x, v)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, v = ctx.saved_tensors
+        R, Cd = x.shape
+        dy = dy.contiguous()
+        dx = _sgemm(dy, v, R, Cd, 1, (1, 1), (1, 1))[0] if ctx.needs_input_grad[0] else None       # dy v^T
+        dv = _sgemm(dy, x, 1, Cd, R, (1, 1), (Cd, 1))[0].view(Cd) if ctx.needs_input_grad[1] else None  # x^T dy
+        return dx, dv
+
+
+def matvec(x, v):
+    return _MatVec.apply(x, v)
 
 
 class _Softmax(torch.autograd.Function):
@@ -595,8 +658,8 @@ def dot(x, w):
     return _Dot.apply(x, w.contiguous())
 
 
-def attn_scores(q, k, M, amax=None):
-    return _AttnScores.apply(q, k, M, amax)
+def attn_scores(q, k, M, amax=None, row_bias=None):
+    return _AttnScores.apply(q, k, M, amax, row_bias)
 
 
 def softmax(S, amax=None, clip=500.0, drop_p=0.0, seed=0, diag=None):
