@@ -195,6 +195,117 @@ __global__ void resize_axis_bwd_kernel(const float* __restrict__ dy, long long o
   }
 }
 
+// float4 flavours: `inner` is a multiple of 4 (all but the innermost axis): one index computation per 4 elements
+__global__ void resize_axis_fwd_v4_kernel(const float4* __restrict__ x, unsigned outer, int Lin, int Lout,
+                                          unsigned inner4, float4* __restrict__ y, int accumulate) {
+  const float scale = (float)Lin / (float)Lout;
+  const unsigned total = outer * (unsigned)Lout * inner4;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned in = idx % inner4, t = idx / inner4;
+    const int j = (int)(t % (unsigned)Lout);
+    const unsigned o = t / (unsigned)Lout;
+    int i0, i1;
+    float w1;
+    src_index(j, scale, Lin, i0, i1, w1);
+    const float4* base = x + (size_t)o * Lin * inner4 + in;
+    const float4 a = __ldg(base + (size_t)i0 * inner4), b = __ldg(base + (size_t)i1 * inner4);
+    const float w0 = 1.f - w1;
+    float4 v = make_float4(w0 * a.x + w1 * b.x, w0 * a.y + w1 * b.y, w0 * a.z + w1 * b.z, w0 * a.w + w1 * b.w);
+    if (accumulate) { const float4 c = y[idx]; v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w; }
+    y[idx] = v;
+  }
+}
+
+__global__ void resize_axis_bwd_v4_kernel(const float4* __restrict__ dy, unsigned outer, int Lin, int Lout,
+                                          unsigned inner4, float4* __restrict__ dx) {
+  const float scale = (float)Lin / (float)Lout, inv = (float)Lout / (float)Lin;
+  const unsigned total = outer * (unsigned)Lin * inner4;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned in = idx % inner4, t = idx / inner4;
+    const int i = (int)(t % (unsigned)Lin);
+    const unsigned o = t / (unsigned)Lin;
+    int jlo = (int)floorf(((float)i - 0.5f) * inv - 0.5f) - 1;
+    int jhi = (int)ceilf(((float)i + 1.5f) * inv - 0.5f) + 1;
+    if (i == 0) jlo = 0;
+    if (i == Lin - 1) jhi = Lout - 1;
+    if (jlo < 0) jlo = 0;
+    if (jhi > Lout - 1) jhi = Lout - 1;
+    const float4* base = dy + (size_t)o * Lout * inner4 + in;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = jlo; j <= jhi; ++j) {
+      int i0, i1;
+      float w1;
+      src_index(j, scale, Lin, i0, i1, w1);
+      float w = 0.f;
+      if (i0 == i) w += 1.f - w1;
+      if (i1 == i) w += w1;
+      if (w != 0.f) {
+        const float4 g = __ldg(base + (size_t)j * inner4);
+        acc.x = fmaf(w, g.x, acc.x); acc.y = fmaf(w, g.y, acc.y); acc.z = fmaf(w, g.z, acc.z); acc.w = fmaf(w, g.w, acc.w);
+      }
+    }
+    dx[idx] = acc;
+  }
+}
+
+// innermost axis (inner == 1): each thread produces 4 consecutive outputs (Lout % 4 == 0) / inputs (Lin % 4 == 0)
+__global__ void resize_last_fwd_kernel(const float* __restrict__ x, unsigned rows, int Lin, int Lout,
+                                       float* __restrict__ y, int accumulate) {
+  const float scale = (float)Lin / (float)Lout;
+  const unsigned q = (unsigned)Lout / 4, total = rows * q;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned r = idx / q;
+    const int j0 = (int)(idx % q) * 4;
+    const float* base = x + (size_t)r * Lin;
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int i0, i1;
+      float w1;
+      src_index(j0 + u, scale, Lin, i0, i1, w1);
+      o[u] = (1.f - w1) * __ldg(base + i0) + w1 * __ldg(base + i1);
+    }
+    float4* dst = reinterpret_cast<float4*>(y + (size_t)r * Lout + j0);
+    float4 v = make_float4(o[0], o[1], o[2], o[3]);
+    if (accumulate) { const float4 c = *dst; v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w; }
+    *dst = v;
+  }
+}
+
+__global__ void resize_last_bwd_kernel(const float* __restrict__ dy, unsigned rows, int Lin, int Lout,
+                                       float* __restrict__ dx) {
+  const float scale = (float)Lin / (float)Lout, inv = (float)Lout / (float)Lin;
+  const unsigned q = (unsigned)Lin / 4, total = rows * q;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned r = idx / q;
+    const int i00 = (int)(idx % q) * 4;
+    const float* base = dy + (size_t)r * Lout;
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i00 + u;
+      int jlo = (int)floorf(((float)i - 0.5f) * inv - 0.5f) - 1;
+      int jhi = (int)ceilf(((float)i + 1.5f) * inv - 0.5f) + 1;
+      if (i == 0) jlo = 0;
+      if (i == Lin - 1) jhi = Lout - 1;
+      if (jlo < 0) jlo = 0;
+      if (jhi > Lout - 1) jhi = Lout - 1;
+      float acc = 0.f;
+      for (int j = jlo; j <= jhi; ++j) {
+        int i0, i1;
+        float w1;
+        src_index(j, scale, Lin, i0, i1, w1);
+        float w = 0.f;
+        if (i0 == i) w += 1.f - w1;
+        if (i1 == i) w += w1;
+        if (w != 0.f) acc = fmaf(w, __ldg(base + j), acc);
+      }
+      o[u] = acc;
+    }
+    *reinterpret_cast<float4*>(dx + (size_t)r * Lin + i00) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ---- class scores of the fused tokens, exact fp32: out[b,k,n] = sum_f W[k,f] vf[b,n,f]; one warp per token ----
 __global__ void token_scores_kernel(const float* __restrict__ vf, const float* __restrict__ W, long long T, int N,
                                     int F, int K, float* __restrict__ out) {
@@ -332,6 +443,19 @@ static int ew_grid(long long total) {
 extern "C" int sx_resize_axis_fwd(const float* x, int64_t outer, int32_t Lin, int32_t Lout, int64_t inner, float* y,
                                   int32_t accumulate, void* stream) {
   const long long big = outer * (Lin > Lout ? Lin : Lout) * inner;
+  const bool a16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (big < (1ll << 31) && a16 && inner % 4 == 0) {
+    resize_axis_fwd_v4_kernel<<<ew_grid(outer * Lout * inner / 4), 256, 0, ST(stream)>>>(
+        (const float4*)x, (unsigned)outer, Lin, Lout, (unsigned)(inner / 4), (float4*)y, accumulate);
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (big < (1ll << 31) && a16 && inner == 1 && Lout % 4 == 0) {
+    resize_last_fwd_kernel<<<ew_grid(outer * Lout / 4), 256, 0, ST(stream)>>>(x, (unsigned)outer, Lin, Lout, y,
+                                                                             accumulate);
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (big < (1ll << 31))
     resize_axis_fwd_kernel<unsigned int><<<ew_grid(outer * Lout * inner), 256, 0, ST(stream)>>>(x, outer, Lin, Lout,
                                                                                                  inner, y, accumulate);
@@ -345,6 +469,18 @@ extern "C" int sx_resize_axis_fwd(const float* x, int64_t outer, int32_t Lin, in
 extern "C" int sx_resize_axis_bwd(const float* dy, int64_t outer, int32_t Lin, int32_t Lout, int64_t inner, float* dx,
                                   void* stream) {
   const long long big = outer * (Lin > Lout ? Lin : Lout) * inner;
+  const bool a16 = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  if (big < (1ll << 31) && a16 && inner % 4 == 0) {
+    resize_axis_bwd_v4_kernel<<<ew_grid(outer * Lin * inner / 4), 256, 0, ST(stream)>>>(
+        (const float4*)dy, (unsigned)outer, Lin, Lout, (unsigned)(inner / 4), (float4*)dx);
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (big < (1ll << 31) && a16 && inner == 1 && Lin % 4 == 0) {
+    resize_last_bwd_kernel<<<ew_grid(outer * Lin / 4), 256, 0, ST(stream)>>>(dy, (unsigned)outer, Lin, Lout, dx);
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (big < (1ll << 31))
     resize_axis_bwd_kernel<unsigned int><<<ew_grid(outer * Lin * inner), 256, 0, ST(stream)>>>(dy, outer, Lin, Lout,
                                                                                                 inner, dx);

@@ -786,6 +786,17 @@ extern "C" int sx_softmax_fwd(const float* S, int64_t R, int32_t L, int64_t lds,
     SX_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
+  if (p_dtype == SX_F32 && L % 4 == 0 && lds % 4 == 0 && ldp % 4 == 0 && al16(S) && al16(P) && L <= 8192) {
+    const int grid = (int)(R < (long long)sms_cached() * 16 ? R : (long long)sms_cached() * 16);
+#define SX_LAUNCH(E_)                                                                                          \
+  softmax_fwd_block<E_><<<grid, 256, 0, ST(stream)>>>(S, R, L, lds, amax, clip, drop_p, seed,                     \
+                                                      (const unsigned long long*)seed_dev, (float*)P, ldp, lse,  \
+                                                      round_tf32, diag)
+    if (L <= 3072) SX_LAUNCH(3); else if (L <= 6144) SX_LAUNCH(6); else SX_LAUNCH(8);
+#undef SX_LAUNCH
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int w = softmax_warps(L, 1);
   SX_REQUIRE(w >= 1, "sx_softmax_fwd: row length %d too large", L);
   const size_t smem = (size_t)w * L * 4;
@@ -814,6 +825,18 @@ extern "C" int sx_softmax_bwd(const float* dP, int64_t ldd, const float* S, int6
                                                                   ldp_fwd, (float*)dS, ldo, round_tf32)
     switch (nv_for(L)) { case 2: SX_LAUNCH(2); break; case 4: SX_LAUNCH(4); break; case 8: SX_LAUNCH(8); break;
                          default: SX_LAUNCH(16); }
+#undef SX_LAUNCH
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (ds_dtype == SX_F32 && L % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ldo % 4 == 0 && al16(S) && al16(dP) &&
+      al16(dS) && L <= 8192) {
+    const int grid = (int)(R < (long long)sms_cached() * 16 ? R : (long long)sms_cached() * 16);
+#define SX_LAUNCH(E_)                                                                                            \
+  softmax_bwd_block<E_><<<grid, 256, 0, ST(stream)>>>(dP, ldd, S, lds, lse, R, L, amax, clip, drop_p, seed,         \
+                                                      (const unsigned long long*)seed_dev, ldp_fwd, (float*)dS, ldo, \
+                                                      round_tf32)
+    if (L <= 3072) SX_LAUNCH(3); else if (L <= 6144) SX_LAUNCH(6); else SX_LAUNCH(8);
 #undef SX_LAUNCH
     SX_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -1005,6 +1028,12 @@ extern "C" int sx_colsum(const void* X, int32_t x_dtype, int64_t R, int32_t C, i
 
 extern "C" int sx_transpose(const float* in, int64_t Z, int32_t R, int32_t C, float* out, void* stream) {
   SX_REQUIRE(Z <= 65535, "sx_transpose: batch %lld too large", (long long)Z);
+  if (R % 4 == 0 && C % 4 == 0 && al16(in) && al16(out)) {
+    dim3 gridv(sx_ceil_div(C, 128), sx_ceil_div(R, 32), (unsigned)Z);
+    transpose_v4_kernel<<<gridv, 256, 0, ST(stream)>>>(in, R, C, out);
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   dim3 grid(sx_ceil_div(C, 32), sx_ceil_div(R, 32), (unsigned)Z), blk(32, 8);
   transpose_kernel<<<grid, blk, 0, ST(stream)>>>(in, R, C, out);
   SX_CHECK_CUDA(cudaGetLastError());

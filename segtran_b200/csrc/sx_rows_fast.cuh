@@ -58,79 +58,83 @@ constexpr int FAST_WARPS = 8;
 // LN + soft aggregate, forward.  Pass 1 per mode: stats + score; pass 2 re-reads the (L2-resident) rows.
 // ------------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(FAST_WARPS * 32)
+__global__ void __launch_bounds__(FAST_WARPS * 32, NV <= 8 ? 2 : 1)
 ln_softaggr_fwd_fast(const float* __restrict__ Y, int B, int M, int N, int F, const float* __restrict__ g,
                      const float* __restrict__ b, const float* __restrict__ ws, const float* __restrict__ bs,
-                     float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev, float* __restrict__ out, float* __restrict__ stats,
-                     float* __restrict__ wts) {
+                     float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                     float* __restrict__ out, float* __restrict__ stats, float* __restrict__ wts) {
   seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
+  __shared__ float s_sc[FAST_WARPS][MAX_MODES], s_mu[FAST_WARPS][MAX_MODES], s_rs[FAST_WARPS][MAX_MODES];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const long long T_ = (long long)B * N;
   for (long long t = (long long)blockIdx.x * FAST_WARPS + warp; t < T_; t += (long long)gridDim.x * FAST_WARPS) {
     const long long bi = t / N, ni = t % N;
-    float sc[MAX_MODES], mu[MAX_MODES], rs[MAX_MODES];
+    // pass 1 (mode loop deliberately not unrolled: one row of registers at a time keeps occupancy high)
+#pragma unroll 1
+    for (int m = 0; m < M; ++m) {
+      const long long ro = (bi * M + m) * N + ni;
+      float4 v[NV];
+      row_load<NV>(v, Y + ro * F, F, lane);
+      if (drop_p > 0.f) {
 #pragma unroll
-    for (int m = 0; m < MAX_MODES; ++m)
-      if (m < M) {
-        const long long ro = (bi * M + m) * N + ni;
-        float4 v[NV];
-        row_load<NV>(v, Y + ro * F, F, lane);
-        if (drop_p > 0.f) {
-#pragma unroll
-          for (int i = 0; i < NV; ++i)
-            if (4 * lane + 128 * i < F) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + 4 * lane + 128 * i));
-        }
-        float mean, rstd;
-        row_mean_rstd<NV>(v, F, lane, mean, rstd);
-        float dot = 0.f;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const int c = 4 * lane + 128 * i;
-          if (c < F) {
-            const float4 gg = ld4(g + c), bb = ld4(b + c), ww = ld4(ws + c);
-            dot += ((v[i].x - mean) * rstd * gg.x + bb.x) * ww.x + ((v[i].y - mean) * rstd * gg.y + bb.y) * ww.y +
-                   ((v[i].z - mean) * rstd * gg.z + bb.z) * ww.z + ((v[i].w - mean) * rstd * gg.w + bb.w) * ww.w;
-          }
-        }
-        sc[m] = sx::warp_sum(dot) + bs[0];
-        mu[m] = mean; rs[m] = rstd;
-        if (lane == 0) { stats[ro * 2] = mean; stats[ro * 2 + 1] = rstd; }
+        for (int i = 0; i < NV; ++i)
+          if (4 * lane + 128 * i < F)
+            v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + 4 * lane + 128 * i));
       }
-    float mx = -3.0e38f;
+      float mean, rstd;
+      row_mean_rstd<NV>(v, F, lane, mean, rstd);
+      float dot = 0.f;
 #pragma unroll
-    for (int m = 0; m < MAX_MODES; ++m) if (m < M) mx = fmaxf(mx, sc[m]);
-    float den = 0.f;
-#pragma unroll
-    for (int m = 0; m < MAX_MODES; ++m) if (m < M) { sc[m] = __expf(sc[m] - mx); den += sc[m]; }
-#pragma unroll
-    for (int m = 0; m < MAX_MODES; ++m) if (m < M) sc[m] /= den;
-    if (lane == 0)
-      for (int m = 0; m < M; ++m) wts[(bi * M + m) * N + ni] = sc[m];
+      for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
+        if (c < F) {
+          const float4 gg = ld4(g + c), bb = ld4(b + c), ww = ld4(ws + c);
+          dot += ((v[i].x - mean) * rstd * gg.x + bb.x) * ww.x + ((v[i].y - mean) * rstd * gg.y + bb.y) * ww.y +
+                 ((v[i].z - mean) * rstd * gg.z + bb.z) * ww.z + ((v[i].w - mean) * rstd * gg.w + bb.w) * ww.w;
+        }
+      }
+      dot = sx::warp_sum(dot) + bs[0];
+      if (lane == 0) {
+        s_sc[warp][m] = dot; s_mu[warp][m] = mean; s_rs[warp][m] = rstd;
+        stats[ro * 2] = mean; stats[ro * 2 + 1] = rstd;
+      }
+    }
+    __syncwarp();
+    float mx = -3.0e38f, den = 0.f;
+    for (int m = 0; m < M; ++m) mx = fmaxf(mx, s_sc[warp][m]);
+    for (int m = 0; m < M; ++m) den += __expf(s_sc[warp][m] - mx);
+    __syncwarp();
+    if (lane < M) {
+      const float w = __expf(s_sc[warp][lane] - mx) / den;
+      s_sc[warp][lane] = w;
+      wts[(bi * M + lane) * N + ni] = w;
+    }
+    __syncwarp();
     float4 o[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int m = 0; m < M; ++m) {
+      const long long ro = (bi * M + m) * N + ni;
+      const float w = s_sc[warp][m], mean = s_mu[warp][m], rstd = s_rs[warp][m];
+      float4 v[NV];
+      row_load<NV>(v, Y + ro * F, F, lane);
 #pragma unroll
-    for (int m = 0; m < MAX_MODES; ++m)
-      if (m < M) {
-        const long long ro = (bi * M + m) * N + ni;
-        float4 v[NV];
-        row_load<NV>(v, Y + ro * F, F, lane);
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const int c = 4 * lane + 128 * i;
-          if (c < F) {
-            if (drop_p > 0.f) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
-            const float4 gg = ld4(g + c), bb = ld4(b + c);
-            const float w = sc[m], mean = mu[m], rstd = rs[m];
-            o[i].x += w * ((v[i].x - mean) * rstd * gg.x + bb.x);
-            o[i].y += w * ((v[i].y - mean) * rstd * gg.y + bb.y);
-            o[i].z += w * ((v[i].z - mean) * rstd * gg.z + bb.z);
-            o[i].w += w * ((v[i].w - mean) * rstd * gg.w + bb.w);
-          }
+      for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
+        if (c < F) {
+          if (drop_p > 0.f) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
+          const float4 gg = ld4(g + c), bb = ld4(b + c);
+          o[i].x += w * ((v[i].x - mean) * rstd * gg.x + bb.x);
+          o[i].y += w * ((v[i].y - mean) * rstd * gg.y + bb.y);
+          o[i].z += w * ((v[i].z - mean) * rstd * gg.z + bb.z);
+          o[i].w += w * ((v[i].w - mean) * rstd * gg.w + bb.w);
         }
       }
+    }
     row_store<NV>(o, out + t * F, F, lane);
+    __syncwarp();
   }
 }
 
@@ -138,85 +142,93 @@ ln_softaggr_fwd_fast(const float* __restrict__ Y, int B, int M, int N, int F, co
 // LN + soft aggregate, backward, row part: dY and the per-(mode,token) score gradient (kept for the column pass)
 // ------------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(FAST_WARPS * 32)
+__global__ void __launch_bounds__(FAST_WARPS * 32, NV <= 8 ? 2 : 1)
 ln_softaggr_bwd_rows_fast(const float* __restrict__ dout, const float* __restrict__ Y, int B, int M, int N, int F,
                           const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ ws,
-                          float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev, const float* __restrict__ stats,
-                          const float* __restrict__ wts, float* __restrict__ dY, float* __restrict__ dscore_out,
-                          float* __restrict__ dbs, int rnd) {
+                          float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                          const float* __restrict__ stats, const float* __restrict__ wts, float* __restrict__ dY,
+                          float* __restrict__ dscore_out, float* __restrict__ dbs, int rnd) {
   seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
+  __shared__ float s_dw[FAST_WARPS][MAX_MODES], s_w[FAST_WARPS][MAX_MODES];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const uint32_t p16 = sx::drop_p16(drop_p);
   const long long T_ = (long long)B * N;
   float dbs_acc = 0.f;
   for (long long t = (long long)blockIdx.x * FAST_WARPS + warp; t < T_; t += (long long)gridDim.x * FAST_WARPS) {
     const long long bi = t / N, ni = t % N;
     float4 go[NV];
     row_load<NV>(go, dout + t * F, F, lane);
-    float dwm[MAX_MODES], w[MAX_MODES];
+#pragma unroll 1
+    for (int m = 0; m < M; ++m) {                       // pass 1: dw_m = <dout, Yn_m>
+      const long long ro = (bi * M + m) * N + ni;
+      const float mean = stats[ro * 2], rstd = stats[ro * 2 + 1];
+      float4 v[NV];
+      row_load<NV>(v, Y + ro * F, F, lane);
+      float dot = 0.f;
 #pragma unroll
-    for (int m = 0; m < MAX_MODES; ++m)
-      if (m < M) {
-        const long long ro = (bi * M + m) * N + ni;
-        const float mean = stats[ro * 2], rstd = stats[ro * 2 + 1];
-        float4 v[NV];
-        row_load<NV>(v, Y + ro * F, F, lane);
-        float dot = 0.f;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const int c = 4 * lane + 128 * i;
-          if (c < F) {
-            if (drop_p > 0.f) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
-            const float4 gg = ld4(g + c), bb = ld4(b + c);
-            dot += go[i].x * ((v[i].x - mean) * rstd * gg.x + bb.x) + go[i].y * ((v[i].y - mean) * rstd * gg.y + bb.y) +
-                   go[i].z * ((v[i].z - mean) * rstd * gg.z + bb.z) + go[i].w * ((v[i].w - mean) * rstd * gg.w + bb.w);
-          }
+      for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
+        if (c < F) {
+          if (drop_p > 0.f) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
+          const float4 gg = ld4(g + c), bb = ld4(b + c);
+          dot += go[i].x * ((v[i].x - mean) * rstd * gg.x + bb.x) + go[i].y * ((v[i].y - mean) * rstd * gg.y + bb.y) +
+                 go[i].z * ((v[i].z - mean) * rstd * gg.z + bb.z) + go[i].w * ((v[i].w - mean) * rstd * gg.w + bb.w);
         }
-        dwm[m] = sx::warp_sum(dot);
-        w[m] = wts[(bi * M + m) * N + ni];
       }
+      dot = sx::warp_sum(dot);
+      if (lane == 0) { s_dw[warp][m] = dot; s_w[warp][m] = wts[(bi * M + m) * N + ni]; }
+    }
+    __syncwarp();
     float wd = 0.f;
+    for (int m = 0; m < M; ++m) wd += s_w[warp][m] * s_dw[warp][m];
+#pragma unroll 1
+    for (int m = 0; m < M; ++m) {                       // pass 2: dY_m
+      const float wm = s_w[warp][m];
+      const float dscore = wm * (s_dw[warp][m] - wd);   // softmax backward over modes
+      dbs_acc += dscore;
+      const long long ro = (bi * M + m) * N + ni;
+      if (lane == 0) dscore_out[ro] = dscore;
+      const float mean = stats[ro * 2], rstd = stats[ro * 2 + 1];
+      float4 v[NV];
+      row_load<NV>(v, Y + ro * F, F, lane);
+      float s1 = 0.f, s2 = 0.f;
+      // v <- normalised row a (dropout applied), go-derived d kept implicitly: d = (wm*go + dscore*ws) * g
 #pragma unroll
-    for (int m = 0; m < MAX_MODES; ++m) if (m < M) wd += w[m] * dwm[m];
-#pragma unroll
-    for (int m = 0; m < MAX_MODES; ++m)
-      if (m < M) {
-        const float dscore = w[m] * (dwm[m] - wd);
-        dbs_acc += dscore;
-        const long long ro = (bi * M + m) * N + ni;
-        if (lane == 0) dscore_out[ro] = dscore;
-        const float mean = stats[ro * 2], rstd = stats[ro * 2 + 1];
-        float4 v[NV], d[NV];
-        row_load<NV>(v, Y + ro * F, F, lane);
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const int c = 4 * lane + 128 * i;
-          d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (c < F) {
-            if (drop_p > 0.f) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
-            const float4 gg = ld4(g + c), ww = ld4(ws + c);
-            v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
-            v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
-            d[i].x = (w[m] * go[i].x + dscore * ww.x) * gg.x; d[i].y = (w[m] * go[i].y + dscore * ww.y) * gg.y;
-            d[i].z = (w[m] * go[i].z + dscore * ww.z) * gg.z; d[i].w = (w[m] * go[i].w + dscore * ww.w) * gg.w;
-            s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
-            s2 += (d[i].x * v[i].x + d[i].y * v[i].y) + (d[i].z * v[i].z + d[i].w * v[i].w);
-          }
-        }
-        s1 = sx::warp_sum(s1) / F; s2 = sx::warp_sum(s2) / F;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const int c = 4 * lane + 128 * i;
-          if (c < F) {
-            float4 r;
-            r.x = rstd * (d[i].x - s1 - v[i].x * s2); r.y = rstd * (d[i].y - s1 - v[i].y * s2);
-            r.z = rstd * (d[i].z - s1 - v[i].z * s2); r.w = rstd * (d[i].w - s1 - v[i].w * s2);
-            if (drop_p > 0.f) r = drop4(r, drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
-            *reinterpret_cast<float4*>(dY + ro * F + c) = rnd4(r, rnd);
-          }
+      for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
+        if (c < F) {
+          if (drop_p > 0.f) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
+          const float4 gg = ld4(g + c), ww = ld4(ws + c);
+          v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
+          v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
+          const float d0 = (wm * go[i].x + dscore * ww.x) * gg.x, d1 = (wm * go[i].y + dscore * ww.y) * gg.y;
+          const float d2 = (wm * go[i].z + dscore * ww.z) * gg.z, d3 = (wm * go[i].w + dscore * ww.w) * gg.w;
+          s1 += (d0 + d1) + (d2 + d3);
+          s2 += (d0 * v[i].x + d1 * v[i].y) + (d2 * v[i].z + d3 * v[i].w);
         }
       }
+      s1 = sx::warp_sum(s1) / F; s2 = sx::warp_sum(s2) / F;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
+        if (c < F) {
+          const float4 gg = ld4(g + c), ww = ld4(ws + c);
+          float4 r;
+          r.x = rstd * ((wm * go[i].x + dscore * ww.x) * gg.x - s1 - v[i].x * s2);
+          r.y = rstd * ((wm * go[i].y + dscore * ww.y) * gg.y - s1 - v[i].y * s2);
+          r.z = rstd * ((wm * go[i].z + dscore * ww.z) * gg.z - s1 - v[i].z * s2);
+          r.w = rstd * ((wm * go[i].w + dscore * ww.w) * gg.w - s1 - v[i].w * s2);
+          if (drop_p > 0.f) {
+            const uint2 h = sx::drop_hash(seed, (unsigned long long)(ro * F + c) >> 2);
+            r.x = sx::drop_keep(h, 0, p16) ? r.x * keep_scale : 0.f; r.y = sx::drop_keep(h, 1, p16) ? r.y * keep_scale : 0.f;
+            r.z = sx::drop_keep(h, 2, p16) ? r.z * keep_scale : 0.f; r.w = sx::drop_keep(h, 3, p16) ? r.w * keep_scale : 0.f;
+          }
+          *reinterpret_cast<float4*>(dY + ro * F + c) = rnd4(r, rnd);
+        }
+      }
+    }
+    __syncwarp();
   }
   if (lane == 0 && dbs_acc != 0.f) atomicAdd(dbs, dbs_acc);
 }
@@ -537,6 +549,151 @@ layernorm_bwd_rows_fast(const float* __restrict__ dy, const float* __restrict__ 
         o.z = rs * (d[i].z - s1 - a[i].z * s2); o.w = rs * (d[i].w - s1 - a[i].w * s2);
         *reinterpret_cast<float4*>(dx + r * C + c) = rnd4(o, rnd);
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax over LONG rows (L up to 1024*EPT): one 256-thread block per row, the row lives in registers
+// (thread t holds float4 columns 4t + 1024 i), block-wide max / sum through warp shuffles + shared memory.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* sbuf) {
+  v = is_max ? sx::warp_max(v) : sx::warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();                                  // sbuf reuse
+  if (lane == 0) sbuf[warp] = v;
+  __syncthreads();
+  float r = (lane < (blockDim.x >> 5)) ? sbuf[lane] : (is_max ? -3.0e38f : 0.f);
+  r = is_max ? sx::warp_max(r) : sx::warp_sum(r);
+  return r;
+}
+
+template <int EPT>
+__global__ void __launch_bounds__(256)
+softmax_fwd_block(const float* __restrict__ S, long long R, int L, long long lds, const float* __restrict__ amax,
+                  float clip, float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                  float* __restrict__ P, long long ldp, float* __restrict__ lse, int rnd, float* __restrict__ diag) {
+  seed += seed_dev ? *seed_dev : 0ull;
+  __shared__ float sbuf[8];
+  const bool do_clip = amax && (*amax > clip);
+  if (diag && amax && blockIdx.x == 0 && threadIdx.x == 0) {
+    diag[0] = fmaxf(diag[0], *amax);
+    if (do_clip) diag[1] += 1.f;
+  }
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+    float4 v[EPT];
+    float m = -3.0e38f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int c = 4 * threadIdx.x + 1024 * i;
+      if (c < L) {
+        v[i] = ld4(S + r * lds + c);
+        if (do_clip) {
+          v[i].x = fminf(fmaxf(v[i].x, -clip), clip); v[i].y = fminf(fmaxf(v[i].y, -clip), clip);
+          v[i].z = fminf(fmaxf(v[i].z, -clip), clip); v[i].w = fminf(fmaxf(v[i].w, -clip), clip);
+        }
+        m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+      }
+    }
+    m = block_reduce(m, true, sbuf);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i)
+      if (4 * threadIdx.x + 1024 * i < L) {
+        v[i].x = __expf(v[i].x - m); v[i].y = __expf(v[i].y - m); v[i].z = __expf(v[i].z - m); v[i].w = __expf(v[i].w - m);
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    sum = block_reduce(sum, false, sbuf);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int c = 4 * threadIdx.x + 1024 * i;
+      if (c < L) {
+        float4 p = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+        if (drop_p > 0.f) p = drop4(p, drop_p, keep_scale, seed, (unsigned long long)(r * ldp + c));
+        *reinterpret_cast<float4*>(P + r * ldp + c) = rnd4(p, rnd);
+      }
+    }
+    if (threadIdx.x == 0 && lse) lse[r] = m + __logf(sum);
+  }
+}
+
+template <int EPT>
+__global__ void __launch_bounds__(256)
+softmax_bwd_block(const float* __restrict__ dP, long long ldd, const float* __restrict__ S, long long lds,
+                  const float* __restrict__ lse, long long R, int L, const float* __restrict__ amax, float clip,
+                  float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                  long long ldp_fwd, float* __restrict__ dS, long long ldo, int rnd) {
+  seed += seed_dev ? *seed_dev : 0ull;
+  __shared__ float sbuf[8];
+  const bool do_clip = amax && (*amax > clip);
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+    const float l = lse[r];
+    float4 p[EPT], gv[EPT];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int c = 4 * threadIdx.x + 1024 * i;
+      if (c < L) {
+        float4 x = ld4(S + r * lds + c);
+        if (do_clip) {
+          x.x = fminf(fmaxf(x.x, -clip), clip); x.y = fminf(fmaxf(x.y, -clip), clip);
+          x.z = fminf(fmaxf(x.z, -clip), clip); x.w = fminf(fmaxf(x.w, -clip), clip);
+        }
+        p[i] = make_float4(__expf(x.x - l), __expf(x.y - l), __expf(x.z - l), __expf(x.w - l));
+        gv[i] = ld4(dP + r * ldd + c);
+        if (drop_p > 0.f) gv[i] = drop4(gv[i], drop_p, keep_scale, seed, (unsigned long long)(r * ldp_fwd + c));
+        dot += (p[i].x * gv[i].x + p[i].y * gv[i].y) + (p[i].z * gv[i].z + p[i].w * gv[i].w);
+      }
+    }
+    dot = block_reduce(dot, false, sbuf);
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int c = 4 * threadIdx.x + 1024 * i;
+      if (c < L) {
+        float4 d = make_float4(p[i].x * (gv[i].x - dot), p[i].y * (gv[i].y - dot), p[i].z * (gv[i].z - dot),
+                               p[i].w * (gv[i].w - dot));
+        if (do_clip) {
+          const float4 raw = ld4(S + r * lds + c);
+          if (raw.x < -clip || raw.x > clip) d.x = 0.f;
+          if (raw.y < -clip || raw.y > clip) d.y = 0.f;
+          if (raw.z < -clip || raw.z > clip) d.z = 0.f;
+          if (raw.w < -clip || raw.w > clip) d.w = 0.f;
+        }
+        *reinterpret_cast<float4*>(dS + r * ldo + c) = rnd4(d, rnd);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched transpose [Z,R,C] -> [Z,C,R], 32 x 128 tiles, float4 global accesses on both sides (R%4==0, C%4==0)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+transpose_v4_kernel(const float* __restrict__ in, int R, int C, float* __restrict__ out) {
+  __shared__ float tile[32][129];
+  const long long z = blockIdx.z;
+  const float* src = in + z * (long long)R * C;
+  float* dst = out + z * (long long)R * C;
+  const int c0 = blockIdx.x * 128, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx * 4;
+    if (r < R && c < C) {
+      const float4 v = ld4(src + (long long)r * C + c);
+      tile[j][tx * 4 + 0] = v.x; tile[j][tx * 4 + 1] = v.y; tile[j][tx * 4 + 2] = v.z; tile[j][tx * 4 + 3] = v.w;
+    }
+  }
+  __syncthreads();
+  const int r4 = (threadIdx.x & 7) * 4;                            // 8 threads cover one 32-float output row segment
+  for (int pass = 0; pass < 4; ++pass) {
+    const int cl = pass * 32 + (threadIdx.x >> 3);
+    const int c = c0 + cl, r = r0 + r4;
+    if (c < C && r < R) {
+      const float4 v = make_float4(tile[r4][cl], tile[r4 + 1][cl], tile[r4 + 2][cl], tile[r4 + 3][cl]);
+      *reinterpret_cast<float4*>(dst + (long long)c * R + r) = v;
     }
   }
 }
