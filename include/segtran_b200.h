@@ -167,6 +167,8 @@ int sx_scale(const float* x, int64_t n, const float* alpha_dev, float alpha, flo
 /* out[z0][c] += sum_{z1,r} X[z1][z0][r][c]  (per-mode bias gradient of MMPrivateOutput in one launch) */
 int sx_colsum_batched(const float* X, int32_t Z1, int64_t stride_z1, int32_t Z0, int64_t stride_z0, int64_t R, int32_t C,
                       int64_t ld, float* out, void* stream);
+/* y = a + b  (residual connection of MMSharedOutput, segtran_shared.py:305) */
+int sx_add(const float* a, const float* b, int64_t n, float* y, void* stream);
 /* out[r % out_mod] += sum_c X[r,c]  (class-bias gradient of the head: rows = (batch, class)) */
 int sx_rowsum(const float* X, int64_t R, int64_t C, int64_t ld, int32_t out_mod, float* out, void* stream);
 /* batched transpose [Z,R,C] -> [Z,C,R] fp32: token flatten / scatter (segtran3d.py:328-330, :478-480) */

@@ -30,9 +30,13 @@ def _grads(module, loss, inputs):
     return gp, gi
 
 
-def gen_encoder(name, dims, M, A, pd, qkb, grid, B, seed, wscale=1.0, mask_p=0.2):
+def gen_encoder(name, dims, M, A, pd, qkb, grid, B, seed, wscale=1.0, mask_p=0.2, squeeze=True, sq_ffn=False,
+                out_type="private"):
     ns = R.load()
     cfg = R.encoder_config(ns.shared, dims=dims, num_modes=M, num_attractors=A, pos_dim=pd, qk_have_bias=qkb)
+    cfg.use_squeezed_transformer = squeeze               # --nosqueeze: plain N x N cross attention per layer
+    cfg.has_FFN_in_squeeze = sq_ffn                      # --squeezeuseffn
+    cfg.trans_output_type = out_type
     enc = R.build_encoder(cfg, seed=seed).eval()
     if wscale != 1.0:                       # push the scores past attn_clip=500 (segtran_shared.py:578-580)
         with torch.no_grad():
@@ -50,10 +54,14 @@ def gen_encoder(name, dims, M, A, pd, qkb, grid, B, seed, wscale=1.0, mask_p=0.2
     with R.quiet():
         y = enc(x, pos, mask, torch.Size(grid))
     gp, gi = _grads(enc, (y * G).sum(), [x])
-    max_attn = [float(t.in_ator_trans.max_attn) for t in enc.translayers] + \
-               [float(t.ator_out_trans.max_attn) for t in enc.translayers]
+    if squeeze:
+        max_attn = [float(t.in_ator_trans.max_attn) for t in enc.translayers] + \
+                   [float(t.ator_out_trans.max_attn) for t in enc.translayers]
+    else:
+        max_attn = [float(t.max_attn) for t in enc.translayers]
     fx = dict(kind="encoder", dims=list(dims), num_modes=M, num_attractors=A, pos_dim=pd, qk_have_bias=qkb,
-              grid=list(grid), x=x.detach(), voxels_pos=pos, vmask=mask, G=G, out=y.detach(),
+              grid=list(grid), use_squeezed_transformer=squeeze, has_FFN_in_squeeze=sq_ffn,
+              trans_output_type=out_type, x=x.detach(), voxels_pos=pos, vmask=mask, G=G, out=y.detach(),
               state_dict={k: v.clone() for k, v in enc.state_dict().items()},
               grad_params=gp, grad_x=gi[0], max_attn=max_attn)
     torch.save(fx, os.path.join(OUT, name + ".pt"))
@@ -156,6 +164,11 @@ def gen_seg2d(name, seed=4):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        gen_encoder("enc2d_nosqueeze", [64, 64], 4, 8, 2, True, (6, 7), 2, seed=21, squeeze=False)
+        gen_encoder("enc3d_sqffn", [64, 64], 4, 16, 3, True, (3, 4, 5), 2, seed=22, sq_ffn=True)
+        gen_encoder("enc3d_sharedout", [64, 64], 4, 16, 3, True, (3, 4, 5), 2, seed=23, out_type="shared")
+        return
     gen_encoder("enc3d_small", [64, 64], 4, 16, 3, True, (3, 4, 5), 2, seed=1)
     gen_encoder("enc2d_compress", [64, 64, 32], 4, 8, 2, False, (6, 7), 2, seed=2)
     gen_encoder("enc3d_clamp", [64, 64], 4, 16, 3, True, (3, 4, 5), 1, seed=7, wscale=60.0)

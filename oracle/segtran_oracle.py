@@ -148,12 +148,12 @@ def cross_att(p: Params, pre: str, in_query: Tensor, in_key: Tensor, num_modes: 
     return (y * w).sum(dim=1)
 
 
-def squeezed_layer(p: Params, pre: str, h: Tensor, num_modes: int, feat_dim: int, **kw) -> Tensor:
-    """SqueezedAttFeatTrans.forward (:809-816): attractors attend to tokens (1 mode, no FFN,
-    config1 :796-799), then tokens attend to the updated attractors (M modes, full FFN)."""
+def squeezed_layer(p: Params, pre: str, h: Tensor, num_modes: int, feat_dim: int, sq_ffn: bool = False, **kw) -> Tensor:
+    """SqueezedAttFeatTrans.forward (:809-816): attractors attend to tokens (1 mode; FFN only with
+    --squeezeuseffn, config1 :796-799), then tokens attend to the updated attractors (M modes, full FFN)."""
     B, N, C = h.shape
     att = p[pre + "attractors"].expand(B, -1, -1)
-    a = cross_att(p, pre + "in_ator_trans.", att, h, 1, C, False, **kw)
+    a = cross_att(p, pre + "in_ator_trans.", att, h, 1, C, sq_ffn, **kw)
     return cross_att(p, pre + "ator_out_trans.", h, a, num_modes, feat_dim, True, **kw)
 
 
@@ -161,7 +161,8 @@ def fusion_encoder(p: Params, pre: str, vfeat: Tensor, voxels_pos: Tensor, vmask
                    translayer_dims: Sequence[int], num_modes: int = 4, *, pos_code_weight: float = 1.0,
                    hid_drop: float = 0.0, att_drop: float = 0.0, training: bool = False,
                    attn_clip: float = 500.0, trans_output_type: str = "private",
-                   collect: Optional[dict] = None) -> Tensor:
+                   collect: Optional[dict] = None, use_squeezed_transformer: bool = True,
+                   has_FFN_in_squeeze: bool = False) -> Tensor:
     """SegtranFusionEncoder.forward (:907-975) with squeezed attention, pos_code_type 'lsinu'.
     vfeat [B,N,C0], voxels_pos [B,N,pd], vmask [B,N,1] (int/bool/float), returns [B,N,C_last]."""
     pe = pos_lsinu(voxels_pos.to(vfeat.dtype), p[pre + "pos_code_layer.pos_coder.pos_fc.weight"],
@@ -176,9 +177,12 @@ def fusion_encoder(p: Params, pre: str, vfeat: Tensor, voxels_pos: Tensor, vmask
         if i == 0:
             h = _dropout(h, hid_drop, training)                                 # :944-945
         h = h * vmask.to(h.dtype)                                               # :946
-        x = squeezed_layer(p, pre + f"translayers.{i}.", h, num_modes, Fd, attn_clip=attn_clip,
-                           att_drop=att_drop, hid_drop=hid_drop, training=training,
-                           trans_output_type=trans_output_type, stats=collect)
+        kw = dict(attn_clip=attn_clip, att_drop=att_drop, hid_drop=hid_drop, training=training,
+                  trans_output_type=trans_output_type, stats=collect)
+        if use_squeezed_transformer:
+            x = squeezed_layer(p, pre + f"translayers.{i}.", h, num_modes, Fd, sq_ffn=has_FFN_in_squeeze, **kw)
+        else:                                     # --nosqueeze (:877-878): plain self cross-attention over all tokens
+            x = cross_att(p, pre + f"translayers.{i}.", h, h, num_modes, Fd, True, **kw)
         layers.append(x)
     if collect is not None:
         collect["layers_vfeat"] = layers

@@ -62,6 +62,7 @@ _PROTOS = {
     "sx_transpose": [_P, _L, _I, _I, _P, _P],
     "sx_colsum_batched": [_P, _I, _L, _I, _L, _L, _I, _L, _P, _P],
     "sx_dot": [_P, _P, _L, _P, _P],
+    "sx_add": [_P, _P, _L, _P, _P],
     "sx_rowsum": [_P, _L, _L, _L, _I, _P, _P],
     "sx_scale": [_P, _L, _P, _F, _P, _P],
     "sx_head_contract_fwd": [_P, _P, _P, _I, _I, _L, _I, _P, _I, _P],

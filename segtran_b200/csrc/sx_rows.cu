@@ -635,6 +635,12 @@ __global__ void rowsum_kernel(const float* __restrict__ X, long long C, long lon
   }
 }
 
+// y = a + b (residual of MMSharedOutput, segtran_shared.py:305), float4 when possible
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = a[i] + b[i];
+}
+
 // y[i] = alpha * x[i]
 __global__ void scale_kernel(const float* __restrict__ x, long long n, const float* __restrict__ alpha_dev, float alpha,
                              float* __restrict__ y) {
@@ -1086,6 +1092,12 @@ extern "C" int sx_seed_derive(const uint64_t* base, uint64_t add, uint64_t* out,
 
 extern "C" int sx_seed_advance(uint64_t* base, uint64_t inc, void* stream) {
   seed_advance_kernel<<<1, 1, 0, ST(stream)>>>((unsigned long long*)base, inc);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_add(const float* a, const float* b, int64_t n, float* y, void* stream) {
+  add_kernel<<<grid_for_rows(n, 256 * 4, sms_cached()), 256, 0, ST(stream)>>>(a, b, n, y);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -8,7 +8,8 @@ checkpoints load with ``load_state_dict``), while every forward runs on the sm_1
 
 Supported configuration = the one the reference's drivers force (train3d.py:174-178, train2d.py:245-249):
 squeezed attention (or plain cross attention), pos_code_type 'lsinu', mid_type 'shared',
-trans_output_type 'private', tie_qk 'shared'|'loose'|'none', pool_modes_feat 'softmax'.  Ablation-only
+trans_output_type 'private'|'shared', tie_qk 'shared'|'loose'|'none', pool_modes_feat 'softmax', plus
+--nosqueeze and --squeezeuseffn.  Ablation-only
 switches (mince, sliding biases, multihead, rand/sinu/none position codes) raise NotImplementedError.
 """
 from __future__ import annotations
@@ -154,9 +155,18 @@ class MMPrivateOutput(nn.Module):
 
 
 class MMSharedOutput(nn.Module):
+    """One Linear(F->F) shared by all modes + residual + dropout + LayerNorm (reference :279-308); here the residual
+    IS kept (:305), unlike MMPrivateOutput."""
+
     def __init__(self, config):
         super().__init__()
-        _unsupported("trans_output_type='shared'")
+        self.num_modes, self.feat_dim = config.num_modes, config.feat_dim
+        self.shared_linear = nn.Linear(self.feat_dim, self.feat_dim)
+        self.resout_norm_layer = nn.LayerNorm(self.feat_dim, eps=1e-12, elementwise_affine=True)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+
+    def forward(self, x, shortcut):             # x, shortcut [B,M,U,F] -> un-normalised sum
+        return ops.add(ops.linear(x, self.shared_linear.weight, self.shared_linear.bias), shortcut)
 
 
 class LearnedSoftAggregate(nn.Module):
@@ -224,7 +234,7 @@ class ExpandedFeatTrans(nn.Module):
                 _unsupported("the no-FFN branch with more than one mode (Polyformer)")
             return ops.layer_norm(u[:, 0], self.first_norm_layer.weight, self.first_norm_layer.bias)
         g = self.intermediate(u)
-        y = self.output(g, None)
+        y = self.output(g, u)
         p = self.output.dropout.p if self.training else 0.0
         ln = self.output.resout_norm_layer
         f2s = self.feat_softaggr.feat2score

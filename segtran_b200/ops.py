@@ -367,6 +367,25 @@ def scale(x, alpha):
     return _Scale.apply(x, float(alpha))
 
 
+class _Add(torch.autograd.Function):
+    """y = a + b (same shapes)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        y = torch.empty_like(a)
+        L.call("sx_add", a.data_ptr(), b.data_ptr(), a.numel(), y.data_ptr(), _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
 class _MatVec(torch.autograd.Function):
     """y[r] = sum_c x[r,c] v[c] on CUDA cores (exact fp32; a K=1 / N=1 product has no business on tensor cores)."""
 

@@ -29,7 +29,13 @@ def oracle_encoder(fx, x=None, dtype=torch.float32, collect=None):
     p = {"voxel_fusion." + k: v.to(dtype) for k, v in fx["state_dict"].items()}
     x = fx["x"] if x is None else x
     return O.fusion_encoder(p, "voxel_fusion.", x.to(dtype), fx["voxels_pos"].to(dtype), fx["vmask"], fx["dims"],
-                            fx["num_modes"], collect=collect), p
+                            fx["num_modes"], collect=collect, **variant_kwargs(fx)), p
+
+
+def variant_kwargs(fx):
+    return dict(use_squeezed_transformer=fx.get("use_squeezed_transformer", True),
+                has_FFN_in_squeeze=fx.get("has_FFN_in_squeeze", False),
+                trans_output_type=fx.get("trans_output_type", "private"))
 
 
 def encoder_config(cfg_cls, *, dims, num_modes=4, num_attractors=16, pos_dim=3, qk_have_bias=True, dropout=0.0):
@@ -49,6 +55,9 @@ def build_b200_encoder(fx, device="cuda", dropout=0.0):
     cfg = encoder_config(S.SegtranConfig, dims=fx["dims"], num_modes=fx["num_modes"],
                          num_attractors=fx["num_attractors"], pos_dim=fx["pos_dim"], qk_have_bias=fx["qk_have_bias"],
                          dropout=dropout)
+    cfg.use_squeezed_transformer = fx.get("use_squeezed_transformer", True)
+    cfg.has_FFN_in_squeeze = fx.get("has_FFN_in_squeeze", False)
+    cfg.trans_output_type = fx.get("trans_output_type", "private")
     enc = S.SegtranFusionEncoder(cfg, "Fusion")
     init = S.SegtranInitWeights(cfg)
     enc.apply(init.tie_qk)

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 OUT_TOL = 1e-3          # max|a-b| / max|b|, forward outputs (north_star tolerance)
 GRAD_TOL = 5e-3         # gradients: same arithmetic (TF32 operands, fp32 accumulation) through ~2x as many GEMMs
-CASES = ["enc3d_small", "enc2d_compress", "enc3d_ragged"]
+CASES = ["enc3d_small", "enc2d_compress", "enc3d_ragged", "enc2d_nosqueeze", "enc3d_sqffn", "enc3d_sharedout"]   # --nosqueeze, --squeezeuseffn, trans_output_type=shared
 
 
 def _run(name, need_grad):

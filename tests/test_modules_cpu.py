@@ -69,7 +69,7 @@ def test_unsupported_ablations_fail_loudly():
     with pytest.raises(NotImplementedError):
         S.SegtranFusionEncoder(cfg, "Fusion")
     cfg = encoder_config(S.SegtranConfig, dims=[32, 32], num_attractors=4)
-    cfg.trans_output_type = "shared"
+    cfg.mid_type = "private"
     with pytest.raises(NotImplementedError):
         S.SegtranFusionEncoder(cfg, "Fusion")
 
