@@ -623,7 +623,8 @@ __global__ void rowsum_kernel(const float* __restrict__ X, long long C, long lon
   const long long r = blockIdx.x;
   const float* x = X + r * ld;
   float acc = 0.f;
-  for (long long c = threadIdx.x; c < C; c += blockDim.x) acc += x[c];
+  for (long long c = (long long)blockIdx.y * blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.y * blockDim.x)
+    acc += x[c];
   acc = sx::warp_sum(acc);
   __shared__ float s[32];
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
@@ -1060,7 +1061,10 @@ extern "C" int sx_scale(const float* x, int64_t n, const float* alpha_dev, float
 
 extern "C" int sx_rowsum(const float* X, int64_t R, int64_t C, int64_t ld, int32_t out_mod, float* out, void* stream) {
   SX_REQUIRE(R >= 1 && R <= 2147483647ll && out_mod >= 1, "sx_rowsum: bad shape");
-  rowsum_kernel<<<(unsigned)R, 512, 0, ST(stream)>>>(X, C, ld, out_mod, out);
+  int chunks = (int)((C + 16383) / 16384);                 // long rows are split over several blocks
+  if (chunks > 64) chunks = 64;
+  if (chunks < 1) chunks = 1;
+  rowsum_kernel<<<dim3((unsigned)R, chunks), 512, 0, ST(stream)>>>(X, C, ld, out_mod, out);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

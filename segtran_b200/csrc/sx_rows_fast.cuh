@@ -248,18 +248,38 @@ ln_softaggr_bwd_cols_fast(const float* __restrict__ dout, const float* __restric
   const long long R = (long long)B * M * N;
   if (c < F) {
     const float4 gg = ld4(g + c), bb = ld4(b + c), ww = ld4(ws + c);
-    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < R; r += (long long)gridDim.y * 8) {
-      const long long bm = r / N, ni = r % N, bi = bm / M;
-      const float mean = stats[r * 2], rstd = stats[r * 2 + 1], w = wts[r], ds = dscore_in[r];
-      float4 v = ld4(Y + r * F + c);
-      if (drop_p > 0.f) v = drop4(v, drop_p, keep_scale, seed, (unsigned long long)(r * F + c));
-      const float4 go = ld4(dout + (bi * N + ni) * F + c);
-      const float a0 = (v.x - mean) * rstd, a1 = (v.y - mean) * rstd, a2 = (v.z - mean) * rstd, a3 = (v.w - mean) * rstd;
-      const float d0 = w * go.x + ds * ww.x, d1 = w * go.y + ds * ww.y, d2 = w * go.z + ds * ww.z, d3 = w * go.w + ds * ww.w;
-      ag.x += d0 * a0; ag.y += d1 * a1; ag.z += d2 * a2; ag.w += d3 * a3;
-      ab.x += d0; ab.y += d1; ab.z += d2; ab.w += d3;
-      aw.x += ds * (a0 * gg.x + bb.x); aw.y += ds * (a1 * gg.y + bb.y);
-      aw.z += ds * (a2 * gg.z + bb.z); aw.w += ds * (a3 * gg.w + bb.w);
+    const long long step = (long long)gridDim.y * 8;
+    for (long long r0 = (long long)blockIdx.y * 8 + threadIdx.y; r0 < R; r0 += 4 * step) {
+      // 4 independent rows per iteration: 8 float4 loads in flight per thread
+      float4 v[4], go[4];
+      float mean[4], rstd[4], w[4], ds[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long r = r0 + u * step;
+        ok[u] = r < R;
+        if (ok[u]) {
+          const long long bm = r / N, ni = r % N, bi = bm / M;
+          mean[u] = stats[r * 2]; rstd[u] = stats[r * 2 + 1]; w[u] = wts[r]; ds[u] = dscore_in[r];
+          v[u] = ld4(Y + r * F + c);
+          go[u] = ld4(dout + (bi * N + ni) * F + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) {
+          const long long r = r0 + u * step;
+          float4 x = v[u];
+          if (drop_p > 0.f) x = drop4(x, drop_p, keep_scale, seed, (unsigned long long)(r * F + c));
+          const float a0 = (x.x - mean[u]) * rstd[u], a1 = (x.y - mean[u]) * rstd[u], a2 = (x.z - mean[u]) * rstd[u],
+                      a3 = (x.w - mean[u]) * rstd[u];
+          const float d0 = w[u] * go[u].x + ds[u] * ww.x, d1 = w[u] * go[u].y + ds[u] * ww.y,
+                      d2 = w[u] * go[u].z + ds[u] * ww.z, d3 = w[u] * go[u].w + ds[u] * ww.w;
+          ag.x += d0 * a0; ag.y += d1 * a1; ag.z += d2 * a2; ag.w += d3 * a3;
+          ab.x += d0; ab.y += d1; ab.z += d2; ab.w += d3;
+          aw.x += ds[u] * (a0 * gg.x + bb.x); aw.y += ds[u] * (a1 * gg.y + bb.y);
+          aw.z += ds[u] * (a2 * gg.z + bb.z); aw.w += ds[u] * (a3 * gg.w + bb.w);
+        }
     }
   }
   __shared__ float4 s[3][8][32];
@@ -466,13 +486,30 @@ ln_param_grad_cols_fast(const float* __restrict__ dy, const float* __restrict__ 
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
   if (c < C)
-    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < R; r += (long long)gridDim.y * 8) {
-      const float mean = stats[r * sstride], rstd = stats[r * sstride + 1];
-      const float4 v = ld4(x + r * C + c), d = ld4(dy + r * C + c);
-      ag.x += d.x * (v.x - mean) * rstd; ag.y += d.y * (v.y - mean) * rstd;
-      ag.z += d.z * (v.z - mean) * rstd; ag.w += d.w * (v.w - mean) * rstd;
-      ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+  {
+    const long long step = (long long)gridDim.y * 8;
+    for (long long r0 = (long long)blockIdx.y * 8 + threadIdx.y; r0 < R; r0 += 4 * step) {
+      float4 v[4], d[4];
+      float mean[4], rstd[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long r = r0 + u * step;
+        ok[u] = r < R;
+        if (ok[u]) {
+          mean[u] = stats[r * sstride]; rstd[u] = stats[r * sstride + 1];
+          v[u] = ld4(x + r * C + c); d[u] = ld4(dy + r * C + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) {
+          ag.x += d[u].x * (v[u].x - mean[u]) * rstd[u]; ag.y += d[u].y * (v[u].y - mean[u]) * rstd[u];
+          ag.z += d[u].z * (v[u].z - mean[u]) * rstd[u]; ag.w += d[u].w * (v[u].w - mean[u]) * rstd[u];
+          ab.x += d[u].x; ab.y += d[u].y; ab.z += d[u].z; ab.w += d[u].w;
+        }
     }
+  }
   __shared__ float4 s[2][8][32];
   s[0][threadIdx.y][threadIdx.x] = ag; s[1][threadIdx.y][threadIdx.x] = ab;
   __syncthreads();

@@ -154,6 +154,7 @@ def test_pos_code_fwd_bwd():
 
 
 @pytest.mark.parametrize("shape,size", [((2, 3, 5, 6, 7), (10, 12, 14)), ((2, 3, 5, 6, 7), (9, 6, 20)),
+                                        ((2, 3, 4, 8, 12), (8, 16, 24)), ((1, 4, 8, 16), (16, 32)),    # x2 / float4 paths
                                         ((1, 2, 8, 9), (16, 27)), ((1, 2, 8, 9), (5, 9))])
 def test_resize_linear_equals_interpolate(shape, size):
     from segtran_b200 import ops
