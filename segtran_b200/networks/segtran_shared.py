@@ -228,13 +228,26 @@ class ExpandedFeatTrans(nn.Module):
         """input_feat [B,U2,C]; attention_probs [B,M,U1,U2] -> [B,U1,F]."""
         M = self.num_modes
         v = ops.linear(input_feat, self.first_linear.weight, self.first_linear.bias)         # [B,U2,M*F]
-        u = ops.attn_pv(attention_probs, v, M)                                               # [B,M,U1,F]
         if not self.has_FFN:
             if M != 1:
                 _unsupported("the no-FFN branch with more than one mode (Polyformer)")
+            u = ops.attn_pv(attention_probs, v, M)                                           # [B,M,U1,F]
             return ops.layer_norm(u[:, 0], self.first_norm_layer.weight, self.first_norm_layer.bias)
-        g = self.intermediate(u)
-        y = self.output(g, u)
+        if isinstance(self.output, MMPrivateOutput) and isinstance(self.intermediate, MMSharedMid):
+            # (P V) Wm^T = P (V Wm^T): push the value bank (U2 rows) through the shared mid Linear instead of the
+            # fused tokens (U1 rows), and fuse MMSharedMid's bias + GELU + dropout into the P.V epilogue.  U itself
+            # is only needed by the (discarded) residual of MMPrivateOutput, so it is never materialised.
+            mid = self.intermediate
+            B, U2 = input_feat.shape[0], input_feat.shape[1]
+            vp = ops.linear(v.view(B, U2, M, self.feat_dim), mid.shared_linear.weight).view(B, U2, M * self.feat_dim)
+            p = mid.dropout.p if self.training else 0.0
+            g = ops.attn_pv_gelu(attention_probs, vp, M, mid.shared_linear.bias, p,
+                                 ops.new_dropout_seed(vp.device) if p > 0 else 0)
+            y = self.output(g, None)
+        else:
+            u = ops.attn_pv(attention_probs, v, M)
+            g = self.intermediate(u)
+            y = self.output(g, u)
         p = self.output.dropout.p if self.training else 0.0
         ln = self.output.resout_norm_layer
         f2s = self.feat_softaggr.feat2score

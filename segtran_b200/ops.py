@@ -475,6 +475,51 @@ class _AttnPV(torch.autograd.Function):
         return dP, dv, None
 
 
+class _AttnPVGelu(torch.autograd.Function):
+    """G[b,m] = dropout(gelu(P[b,m] V'[b,:,m] + bias)) — the P.V contraction with MMSharedMid's bias / erf-GELU /
+    dropout fused into its epilogue.  V' = V Wm^T is the value bank already pushed through the shared mid Linear
+    (re-association (P V) Wm^T = P (V Wm^T): A rows instead of N, see ExpandedFeatTrans.forward)."""
+
+    @staticmethod
+    def forward(ctx, P, v, M, bias, drop_p, seed):
+        B, _, U1, U2 = P.shape
+        Fd = v.shape[-1] // M
+        P = _rowpad(P)
+        vv = v.view(B, U2, M, Fd).permute(0, 2, 3, 1)
+        G = torch.empty((B, M, U1, Fd), device=P.device, dtype=torch.float32)
+        H = torch.empty_like(G)
+        gemm_nt(P, vv, out=G, bias=bias, gelu=True, preact=H, drop_p=drop_p, seed=seed)
+        ctx.save_for_backward(P, v, H)
+        ctx.meta = (M, Fd, drop_p, bias is not None)
+        ctx.seed = seed
+        return G
+
+    @staticmethod
+    def backward(ctx, dG):
+        P, v, H = ctx.saved_tensors
+        M, Fd, drop_p, has_b = ctx.meta
+        B, _, U1, U2 = P.shape
+        dG = dG.contiguous()
+        dH = torch.empty_like(dG)
+        L.call("sx_gelu_bwd", dG.data_ptr(), H.data_ptr(), L.SX_F32, dG.numel(), drop_p, *_seed_args(ctx.seed),
+               dH.data_ptr(), L.SX_F32, 1, _stream())
+        dP = dv = db = None
+        if ctx.needs_input_grad[0]:
+            dP = _rowpad_empty((B, M, U1, U2), P.device)
+            gemm_nt(dH, v.view(B, U2, M, Fd).permute(0, 2, 1, 3), out=dP, round_out=False)
+        if ctx.needs_input_grad[1]:
+            dv = torch.empty_like(v)
+            gemm_nt(P.transpose(-1, -2), dH.transpose(-1, -2), out=dv.view(B, U2, M, Fd).permute(0, 2, 1, 3),
+                    round_out=False)
+        if has_b and ctx.needs_input_grad[3]:
+            db = colsum(dH.view(-1, Fd))
+        return dP, dv, None, db, None, None
+
+
+def attn_pv_gelu(P, v, M, bias, drop_p=0.0, seed=0):
+    return _AttnPVGelu.apply(P, v, M, bias, drop_p, seed)
+
+
 class _LayerNorm(torch.autograd.Function):
     """nn.LayerNorm(C, eps=1e-12, affine) over the last dim (first_norm_layer, segtran_shared.py:456)."""
 
