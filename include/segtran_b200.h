@@ -85,6 +85,8 @@ typedef struct {
   uint32_t _pad3;
   uint64_t drop_seed;            /* counter-based mask: keep(idx) = hash(seed, flat index in C) >= p */
   const uint64_t* drop_seed_dev; /* optional device seed added to drop_seed (CUDA-graph safe) */
+  const float* addend;           /* optional fp32 tensor in C's layout: C = epilogue(alpha*A.B^T + addend); used by the
+                                    error-compensated 3-pass TF32 mode (A_hi B_hi + A_lo B_hi + A_hi B_lo) */
 } sx_gemm_args;
 
 int sx_gemm(const sx_gemm_args* args, void* stream);

@@ -54,6 +54,7 @@ struct GemmParams {
   float drop_p;
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_dev;
+  const float* addend;   // optional fp32 tensor in C's layout added to alpha*acc before bias/activation (tf32x3 passes)
   // descriptor fields (bring-up knobs; defaults are the canonical encodings)
   unsigned int lbo_k, sbo_k, lbo_mn_a, lbo_mn_b, sbo_mn, desc_version;
   int dbg_epi;      // bring-up: 0 normal, 1 skip global stores, 2 skip TMEM loads too
@@ -304,6 +305,24 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           f[i] = __uint_as_float(va[i]) * p.alpha + bias_m[(i >> 1) & 1];
           f[16 + i] = __uint_as_float(vb[i]) * p.alpha + bias_m[2 + ((i >> 1) & 1)];
         }
+        if (p.addend) {
+#pragma unroll
+          for (int P = 0; P < 2; ++P)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int grow = row0 + 16 * P + 8 * h + tr;
+              if (grow < p.M) {
+                const float* ar = p.addend + zoff + (long long)grow * p.ldc;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                  for (int e = 0; e < 2; ++e) {
+                    const int col = col0 + 8 * j + tc + e;
+                    if (col < p.N) f[16 * P + 4 * j + 2 * h + e] += ar[col];
+                  }
+              }
+            }
+        }
         if (add_bias && p.bias_mode == SX_BIAS_N) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -536,6 +555,8 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
   p.alpha = a->alpha; p.bias_mode = a->bias ? a->bias_mode : SX_BIAS_NONE; p.bias = a->bias;
   p.bias_sz0 = a->bias_stride_z0; p.bias_sz1 = a->bias_stride_z1;
   p.act = a->act; p.accumulate = a->accumulate; p.preact = a->preact; p.amax = a->amax;
+  p.addend = a->addend;
+  SX_REQUIRE(!a->addend || (p.split_k == 1 && !a->accumulate && a->c_dtype == SX_F32), "sx_gemm: addend needs split_k=1, accumulate=0, fp32 C");
   p.drop_p = a->drop_p; p.drop_seed = a->drop_seed;
   p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(a->drop_seed_dev);
   p.lbo_k = (unsigned)g_knobs.lbo_k; p.sbo_k = (unsigned)g_knobs.sbo_k; p.sbo_mn = (unsigned)(g_knobs.sbo_mn >= 0 ? g_knobs.sbo_mn : (es == 4 ? 512 : 1024));

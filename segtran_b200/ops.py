@@ -17,20 +17,29 @@ from . import _lib as L
 # ------------------------------------------------------------------------------------------------
 # precision policy
 # ------------------------------------------------------------------------------------------------
-# "tf32": activations/weights stay fp32 in HBM, tensor cores consume them as TF32 (operands pre-rounded
-#         to nearest so the hardware truncation is exact) with fp32 accumulation — parity-grade (<=1e-3).
+# "tf32":   activations/weights stay fp32 in HBM, tensor cores consume them as TF32 (operands pre-rounded
+#           to nearest so the hardware truncation is exact) with fp32 accumulation — parity-grade (<=1e-3).
+# "tf32x3": validation mode.  No producer rounds; every GEMM runs as three TF32 passes on the split operands
+#           (A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32 accumulate), which recovers fp32-level products (~1e-6).
+#           3x the tensor work plus the operand splits — used by the parity tests to show that the kernels and
+#           the re-associated algebra are exact and TF32 operand rounding is the only deviation of the fast mode.
 _PRECISION = "tf32"
 
 
 def set_precision(p: str):
     global _PRECISION
-    if p not in ("tf32",):
-        raise ValueError("unsupported precision %r (this build implements 'tf32')" % (p,))
+    if p not in ("tf32", "tf32x3"):
+        raise ValueError("unsupported precision %r (this build implements 'tf32' and 'tf32x3')" % (p,))
     _PRECISION = p
 
 
 def get_precision() -> str:
     return _PRECISION
+
+
+def _rt() -> int:
+    """round-to-TF32 flag handed to producer kernels (off in the 3-pass validation mode)."""
+    return 1 if _PRECISION == "tf32" else 0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -142,11 +151,11 @@ def _pick_split_k(M, N, K, Z, bk=32, sms=148, epi=10):
     return best
 
 
-def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, alpha: float = 1.0,
-            bias: Optional[torch.Tensor] = None, bias_mode: int = L.SX_BIAS_N, gelu: bool = False,
-            preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
-            amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
-            reduce_z1: bool = False) -> torch.Tensor:
+def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, alpha: float = 1.0,
+               bias: Optional[torch.Tensor] = None, bias_mode: int = L.SX_BIAS_N, gelu: bool = False,
+               preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
+               amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
+               reduce_z1: bool = False, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a [..., M, K], b [..., N, K] (strided fp32 views; either dim may be the contiguous one) ->
     out [z1, z0, M, N] fp32.  With reduce_z1 the z1 batch dim is summed into one output (atomic accumulate)."""
     _req_cuda(a, b, out, bias, preact, amax)
@@ -180,7 +189,7 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = N
     g.B = _operand(b4, Z1, Z0, "B")
     g.C = o4.data_ptr()
     g.c_dtype = L.SX_F32
-    g.round_tf32 = 1 if round_out else 0
+    g.round_tf32 = 1 if (round_out and _PRECISION == "tf32") else 0
     g.ldc = o4.stride(-2)
     g.c_stride_z0 = o4.stride(1) if o4.shape[1] > 1 else 0
     g.c_stride_z1 = 0 if reduce_z1 else (o4.stride(0) if o4.shape[0] > 1 else 0)
@@ -202,8 +211,55 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = N
         g.amax = amax.data_ptr()
     g.drop_p = drop_p
     g.drop_seed, g.drop_seed_dev = _seed_args(seed)
+    if addend is not None:
+        g.addend = addend.data_ptr()
     L.call("sx_gemm", C.byref(g), _stream())
     return out
+
+
+def _tf32_split(t: torch.Tensor):
+    """fp32 view -> (hi, lo) with the same strides: hi = TF32(t), lo = TF32(t - hi)   (tf32x3 validation mode)."""
+    if any(st == 0 and sz > 1 for st, sz in zip(t.stride(), t.shape)):
+        t = t.contiguous()
+    hi = torch.empty_strided(t.size(), t.stride(), device=t.device, dtype=torch.float32)
+    hi.copy_(t)
+    hi.view(torch.int32).add_(0x1000).bitwise_and_(-8192)
+    lo = torch.empty_strided(t.size(), t.stride(), device=t.device, dtype=torch.float32)
+    torch.sub(t, hi, out=lo)
+    lo.view(torch.int32).add_(0x1000).bitwise_and_(-8192)
+    return hi, lo
+
+
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, alpha: float = 1.0,
+            bias: Optional[torch.Tensor] = None, bias_mode: int = L.SX_BIAS_N, gelu: bool = False,
+            preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
+            amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
+            reduce_z1: bool = False) -> torch.Tensor:
+    """C[..., m, n] = epilogue(alpha * sum_k a[..., m, k] b[..., n, k]) on the tcgen05 GEMM.  In the default
+    precision this is one launch; in 'tf32x3' it is three passes on the hi/lo operand splits."""
+    if _PRECISION == "tf32":
+        return _gemm_nt_1(a, b, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
+                          accumulate=accumulate, split_k=split_k, amax=amax, drop_p=drop_p, seed=seed,
+                          round_out=round_out, reduce_z1=reduce_z1)
+    _req_cuda(a, b)
+    ah, al = _tf32_split(a)
+    bh, bl = _tf32_split(b)
+    if accumulate or reduce_z1:              # linear epilogue: the three passes simply accumulate into C
+        out = _gemm_nt_1(al, bh, out=out, alpha=alpha, accumulate=accumulate, reduce_z1=reduce_z1, split_k=1,
+                         round_out=False)
+        _gemm_nt_1(ah, bl, out=out, alpha=alpha, accumulate=True, reduce_z1=reduce_z1, split_k=1, round_out=False)
+        return _gemm_nt_1(ah, bh, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, accumulate=True,
+                          reduce_z1=reduce_z1, split_k=1, round_out=False)
+    a4, b4 = _as4(a), _as4(b)
+    if out is None:
+        out = torch.empty((max(a4.shape[0], b4.shape[0]), max(a4.shape[1], b4.shape[1]), a4.shape[-2], b4.shape[-2]),
+                          device=a.device, dtype=torch.float32)
+    o4 = _as4(out)
+    part = torch.empty_strided(o4.size(), o4.stride(), device=a.device, dtype=torch.float32)    # C's layout
+    _gemm_nt_1(al, bh, out=part, alpha=alpha, split_k=1, round_out=False)
+    _gemm_nt_1(ah, bl, out=part, alpha=alpha, split_k=1, round_out=False, addend=part)
+    return _gemm_nt_1(ah, bh, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
+                      split_k=1, amax=amax, drop_p=drop_p, seed=seed, round_out=False, addend=part)
 
 
 def _pad4(n: int) -> int:
@@ -241,6 +297,8 @@ def round_tf32(x: torch.Tensor) -> torch.Tensor:
     """fp32 -> fp32 rounded to the nearest TF32 value (weights, once per step)."""
     _req_cuda(x)
     x = x.contiguous()
+    if _PRECISION != "tf32":
+        return x
     y = torch.empty_like(x)
     L.call("sx_convert", x.data_ptr(), L.SX_F32, x.numel(), y.data_ptr(), L.SX_F32, 1, _stream())
     return y
@@ -283,7 +341,7 @@ class _Linear(torch.autograd.Function):
         if gelu:
             dh = torch.empty_like(dy2)
             L.call("sx_gelu_bwd", dy2.data_ptr(), h.data_ptr(), L.SX_F32, dy2.numel(), drop_p, *_seed_args(seed), dh.data_ptr(),
-                   L.SX_F32, 1, _stream())
+                   L.SX_F32, _rt(), _stream())
             dy2 = dh
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
@@ -423,7 +481,7 @@ class _Softmax(torch.autograd.Function):
         P = _rowpad_empty(S.shape, S.device)
         lse = torch.empty(R, device=S.device, dtype=torch.float32)
         L.call("sx_softmax_fwd", S.data_ptr(), R, Lr, ld, _ptr(amax), clip, drop_p, *_seed_args(seed), P.data_ptr(), L.SX_F32,
-               P.stride(-2), 1, lse.data_ptr(), _ptr(diag), _stream())
+               P.stride(-2), _rt(), lse.data_ptr(), _ptr(diag), _stream())
         ctx.save_for_backward(S, lse, amax)
         ctx.meta = (clip, drop_p, seed, P.stride(-2))
         return P
@@ -437,7 +495,7 @@ class _Softmax(torch.autograd.Function):
         R = S.numel() // Lr
         dS = _rowpad_empty(S.shape, S.device)
         L.call("sx_softmax_bwd", dP.data_ptr(), dP.stride(-2), S.data_ptr(), S.stride(-2), lse.data_ptr(), R, Lr,
-               _ptr(amax), clip, drop_p, *_seed_args(seed), ldp, dS.data_ptr(), L.SX_F32, dS.stride(-2), 1, _stream())
+               _ptr(amax), clip, drop_p, *_seed_args(seed), ldp, dS.data_ptr(), L.SX_F32, dS.stride(-2), _rt(), _stream())
         return dS, None, None, None, None, None
 
 
@@ -502,7 +560,7 @@ class _AttnPVGelu(torch.autograd.Function):
         dG = dG.contiguous()
         dH = torch.empty_like(dG)
         L.call("sx_gelu_bwd", dG.data_ptr(), H.data_ptr(), L.SX_F32, dG.numel(), drop_p, *_seed_args(ctx.seed),
-               dH.data_ptr(), L.SX_F32, 1, _stream())
+               dH.data_ptr(), L.SX_F32, _rt(), _stream())
         dP = dv = db = None
         if ctx.needs_input_grad[0]:
             dP = _rowpad_empty((B, M, U1, U2), P.device)
@@ -530,7 +588,7 @@ class _LayerNorm(torch.autograd.Function):
         R = x.numel() // Cd
         y = torch.empty_like(x)
         stats = torch.empty((R, 2), device=x.device, dtype=torch.float32)
-        L.call("sx_layernorm_fwd", x.data_ptr(), R, Cd, g.data_ptr(), b.data_ptr(), y.data_ptr(), L.SX_F32, 1,
+        L.call("sx_layernorm_fwd", x.data_ptr(), R, Cd, g.data_ptr(), b.data_ptr(), y.data_ptr(), L.SX_F32, _rt(),
                stats.data_ptr(), _stream())
         ctx.save_for_backward(x, g, stats)
         return y
@@ -545,7 +603,7 @@ class _LayerNorm(torch.autograd.Function):
         dg = torch.zeros_like(g)
         db = torch.zeros_like(g)
         L.call("sx_layernorm_bwd", dy.data_ptr(), x.data_ptr(), R, Cd, g.data_ptr(), stats.data_ptr(), dx.data_ptr(),
-               L.SX_F32, 1, dg.data_ptr(), db.data_ptr(), _stream())
+               L.SX_F32, _rt(), dg.data_ptr(), db.data_ptr(), _stream())
         return dx, dg, db
 
 
@@ -609,7 +667,7 @@ class _LnSoftAggr(torch.autograd.Function):
         dbs = torch.zeros(1, device=Y.device, dtype=torch.float32)
         scratch = torch.empty(B * M * N, device=Y.device, dtype=torch.float32)
         L.call("sx_ln_softaggr_bwd", dout.data_ptr(), Y.data_ptr(), B, M, N, Fd, g.data_ptr(), b.data_ptr(),
-               ws.data_ptr(), drop_p, *_seed_args(seed), stats.data_ptr(), wts.data_ptr(), dY.data_ptr(), L.SX_F32, 1, dg.data_ptr(),
+               ws.data_ptr(), drop_p, *_seed_args(seed), stats.data_ptr(), wts.data_ptr(), dY.data_ptr(), L.SX_F32, _rt(), dg.data_ptr(),
                db.data_ptr(), dws.data_ptr(), dbs.data_ptr(), scratch.data_ptr(), _stream())
         return dY, dg, db, dws.view(ws_shape), dbs.view(bs_shape), None, None
 
@@ -658,7 +716,7 @@ class _Prologue(torch.autograd.Function):
         h = torch.empty_like(x)
         stats = torch.empty((B * N, 4), device=x.device, dtype=torch.float32)
         L.call("sx_prologue_fwd", x.data_ptr(), B, N, Cd, g.data_ptr(), b.data_ptr(), pe.data_ptr(), C0, pe_bstride,
-               posw, _ptr(mask), drop_p, *_seed_args(seed), h.data_ptr(), L.SX_F32, 1, stats.data_ptr(), _stream())
+               posw, _ptr(mask), drop_p, *_seed_args(seed), h.data_ptr(), L.SX_F32, _rt(), stats.data_ptr(), _stream())
         ctx.save_for_backward(x, g, b, pe, mask, stats)
         ctx.meta = (posw, drop_p, seed, pe_bstride)
         return h

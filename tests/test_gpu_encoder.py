@@ -50,6 +50,32 @@ def test_backward_matches_reference(name):
         assert err <= GRAD_TOL * float(g.abs().max()) + 2e-5 * gscale, (k, err, float(g.abs().max()))
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_tf32x3_mode_matches_reference_to_fp32_level(name):
+    """Validation mode (ops.set_precision('tf32x3')): no producer rounds to TF32 and every GEMM runs as three passes on
+    the hi/lo operand splits.  Forward and gradients then agree with the reference to fp32 round-off, which shows that
+    the kernels, the fused epilogues and the re-associated algebra are exact and that TF32 operand rounding is the
+    only deviation of the default mode."""
+    from segtran_b200 import ops
+    ops.set_precision("tf32x3")
+    try:
+        fx, enc, x, y = _run(name, True)
+        e = rel_err(y, fx["out"])
+        (y * fx["G"].cuda()).sum().backward()
+        ex = rel_err(x.grad, fx["grad_x"])
+        print(name, "tf32x3 fwd rel %.2e dx rel %.2e" % (e, ex))
+        assert e < 2e-5 and ex < 1e-4
+        gscale = max(float(g.abs().max()) for g in fx["grad_params"].values())
+        got = dict(enc.named_parameters())
+        for k, g in fx["grad_params"].items():
+            if float(g.abs().max()) == 0.0:
+                continue
+            err = float((got[k].grad.cpu() - g).abs().max())
+            assert err <= 1e-4 * float(g.abs().max()) + 1e-6 * gscale, (k, err, float(g.abs().max()))
+    finally:
+        ops.set_precision("tf32")
+
+
 def test_clamp_case_matches_reference():
     """Scores beyond attn_clip=500 (segtran_shared.py:578-580): squeeze-out max is ~6000 -> clamped, in-squeeze
     (max 477) is not.  Softmax over saturated scores amplifies operand rounding, hence the looser bound."""
@@ -59,6 +85,15 @@ def test_clamp_case_matches_reference():
     assert t.ator_out_trans.clamp_count == 1 and t.in_ator_trans.clamp_count == 0
     assert abs(t.ator_out_trans.max_attn - fx["max_attn"][1]) < 1e-2 * fx["max_attn"][1]
     assert rel_err(y, fx["out"]) < 5e-2
+    from segtran_b200 import ops
+    ops.set_precision("tf32x3")          # with fp32-level products the saturated softmax agrees tightly too
+    try:
+        with torch.no_grad():
+            fx, enc, x, y = _run("enc3d_clamp", False)
+        print("clamp tf32x3 rel", rel_err(y, fx["out"]))
+        assert rel_err(y, fx["out"]) < 1e-3
+    finally:
+        ops.set_precision("tf32")
 
 
 def test_training_mode_dropout_runs_and_is_consistent():

@@ -117,6 +117,17 @@ def test_2d_config_stacks_match_oracle(dims, A, grid, qkb):
     e = rel_err(y, ref)
     print("dims %s: max-rel %.3e rms-rel %.3e" % (dims, e, rms_rel(y, ref)))
     assert e < 1e-3
+    # the same stack in the 3-pass validation mode: fp32-level agreement (TF32 rounding is the only deviation above)
+    from segtran_b200 import ops
+    ops.set_precision("tf32x3")
+    try:
+        with torch.no_grad():
+            y3 = enc(x.cuda(), pos.cuda(), mask.cuda(), torch.Size(grid))
+    finally:
+        ops.set_precision("tf32")
+    e3 = rel_err(y3, ref)
+    print("dims %s tf32x3: max-rel %.3e" % (dims, e3))
+    assert e3 < 5e-5
     # gradients flow and are finite at these widths
     xg = x.cuda().requires_grad_()
     enc.train()

@@ -43,6 +43,35 @@ def test_gemm_nt_all_majors_and_batch():
     close(red[0].double(), ref.sum(0), 1e-5)
 
 
+def test_gemm_nt_tf32x3_recovers_fp32_products():
+    """The 3-pass validation mode (A_hi B_hi + A_lo B_hi + A_hi B_lo) on UN-rounded fp32 operands: ~1e-6 of the fp64
+    product, for every operand majorness, with the fused epilogue (bias + GELU + preact) and the accumulate path."""
+    from segtran_b200 import ops
+    a = torch.randn(2, 3, 152, 264, device="cuda")
+    b = torch.randn(2, 3, 260, 264, device="cuda")
+    bias = torch.randn(260, device="cuda")
+    ref = a.double() @ b.double().transpose(-1, -2)
+    e1 = float((ops.gemm_nt(a, b, round_out=False).double() - ref).abs().max() / ref.abs().max())
+    ops.set_precision("tf32x3")
+    try:
+        am = a.transpose(-1, -2).contiguous().transpose(-1, -2)
+        bm = b.transpose(-1, -2).contiguous().transpose(-1, -2)
+        for x, y in ((a, b), (am, bm), (a, bm), (am, b)):
+            close(ops.gemm_nt(x, y).double(), ref, 2e-6)
+        h = torch.empty(2, 3, 152, 260, device="cuda")
+        g = ops.gemm_nt(a, b, bias=bias, gelu=True, preact=h)
+        close(h.double(), ref + bias.double(), 2e-6)
+        close(g.double(), torch.nn.functional.gelu(ref + bias.double()), 2e-6)
+        red = ops.gemm_nt(am, bm, reduce_z1=True)
+        close(red[0].double(), ref.sum(0), 2e-6)
+        acc = torch.ones(2, 3, 152, 260, device="cuda")
+        ops.gemm_nt(a, b, out=acc, accumulate=True, alpha=0.5)
+        close(acc.double(), 1.0 + 0.5 * ref, 2e-6)
+    finally:
+        ops.set_precision("tf32")
+    assert e1 > 1e-5          # the single-pass mode on un-rounded operands is visibly TF32
+
+
 def test_linear_fwd_bwd_gelu():
     from segtran_b200 import ops
     x = torch.randn(5, 37, 96, device="cuda", requires_grad=True)
