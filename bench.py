@@ -251,7 +251,7 @@ def run_b200(args):
         list(net.out_conv3d.parameters())
     use_graph = not args.no_graph
     # with a captured step the all-reduce runs after the replay (NCCL is kept out of the graph); eager mode overlaps it
-    bucket = GradBucket(hot_params, overlap_chunks=0 if use_graph else 4)
+    bucket = GradBucket(hot_params, overlap_chunks=0 if use_graph else 4, direct_accumulate=use_graph)
     B, S, K = CFG["B"], CFG["S"], CFG["classes"]
     feat = torch.randn(B, CFG["C0"], *CFG["grid"], device=dev).requires_grad_()
     curr = torch.randn(B, CFG["Cf"], *CFG["sp1"], device=dev).requires_grad_()

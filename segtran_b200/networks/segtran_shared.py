@@ -441,8 +441,9 @@ class SegtranPosEncoder(nn.Module):
         """voxels_pos [B,N,pd] -> code [N,C0] when the batch shares one set of positions (stride-0 batch dim or
         B == 1), else [B,N,C0].  The global max of the whole tensor normalises the positions (:1231)."""
         key = tuple(voxels_pos.shape)              # shape-keyed like the reference's cache (:1219)
-        if not self.training and self.cached_pos_code is not None and self.cached_feat_shape == key:
-            return self.cached_pos_code
+        if not self.training and self.cached_pos_code is not None and self.cached_feat_shape == key and \
+                not (torch.is_grad_enabled() and self.cached_pos_code.requires_grad):
+            return self.cached_pos_code        # (a cached code that still carries a graph is rebuilt, not re-used)
         B, N, pd = voxels_pos.shape
         shared = B == 1 or voxels_pos.stride(0) == 0
         pos2d = voxels_pos[0] if shared else voxels_pos.reshape(B * N, pd)

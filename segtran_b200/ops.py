@@ -37,6 +37,36 @@ def get_precision() -> str:
     return _PRECISION
 
 
+# Direct gradient accumulation (opt-in, used by parallel.GradBucket(direct_accumulate=True)): when a weight is a leaf
+# whose .grad already exists (a view into the flat gradient bucket), the weight-gradient GEMM / bias column sum
+# accumulates straight into it and autograd receives None for that input — this removes the zero-fill of a temporary
+# and the AccumulateGrad add (two extra passes over every weight gradient).  Post-accumulate hooks do not fire.
+_GRAD_SINK = False
+
+
+def set_grad_sink(on: bool):
+    global _GRAD_SINK
+    _GRAD_SINK = bool(on)
+
+
+def _grad_target(p):
+    if not _GRAD_SINK or not isinstance(p, torch.nn.Parameter) or p.grad is None:
+        return None
+    g = p.grad
+    if g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape or not g.is_cuda:
+        return None
+    return g
+
+
+def _sink_or_zeros(p, like=None):
+    """-> (buffer the kernel accumulates into, gradient to hand to autograd or None when it went straight to p.grad)."""
+    tgt = _grad_target(p)
+    if tgt is not None:
+        return tgt, None
+    z = torch.zeros_like(p if like is None else like)
+    return z, z
+
+
 def _rt() -> int:
     """round-to-TF32 flag handed to producer kernels (off in the 3-pass validation mode)."""
     return 1 if _PRECISION == "tf32" else 0
@@ -331,6 +361,7 @@ class _Linear(torch.autograd.Function):
         gemm_nt(x2, Wr, out=y, bias=b, gelu=gelu, preact=h, drop_p=drop_p, seed=seed)
         ctx.save_for_backward(x2, Wr, h)
         ctx.meta = (shp, b is not None, gelu, drop_p, seed)
+        ctx.leaves = (W, b)
         return y.view(*shp[:-1], O)
 
     @staticmethod
@@ -346,10 +377,19 @@ class _Linear(torch.autograd.Function):
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = gemm_nt(dy2, Wr.t(), round_out=False).view(shp)
+        W, b = ctx.leaves
         if ctx.needs_input_grad[1]:
-            dW = gemm_nt(dy2.t(), x2.t(), round_out=False).view(Wr.shape)
+            tgt = _grad_target(W)
+            if tgt is not None:
+                gemm_nt(dy2.t(), x2.t(), out=tgt, accumulate=True, round_out=False)
+            else:
+                dW = gemm_nt(dy2.t(), x2.t(), round_out=False).view(Wr.shape)
         if has_b and ctx.needs_input_grad[2]:
-            db = colsum(dy2)
+            tgt = _grad_target(b)
+            if tgt is not None:
+                colsum(dy2, out=tgt)
+            else:
+                db = colsum(dy2)
         return dx, dW, db, None, None, None
 
 
@@ -591,6 +631,7 @@ class _LayerNorm(torch.autograd.Function):
         L.call("sx_layernorm_fwd", x.data_ptr(), R, Cd, g.data_ptr(), b.data_ptr(), y.data_ptr(), L.SX_F32, _rt(),
                stats.data_ptr(), _stream())
         ctx.save_for_backward(x, g, stats)
+        ctx.leaves = (g, b)
         return y
 
     @staticmethod
@@ -600,10 +641,10 @@ class _LayerNorm(torch.autograd.Function):
         Cd = x.shape[-1]
         R = x.numel() // Cd
         dx = torch.empty_like(x)
-        dg = torch.zeros_like(g)
-        db = torch.zeros_like(g)
+        dgb, dg = _sink_or_zeros(ctx.leaves[0])
+        dbb, db = _sink_or_zeros(ctx.leaves[1])
         L.call("sx_layernorm_bwd", dy.data_ptr(), x.data_ptr(), R, Cd, g.data_ptr(), stats.data_ptr(), dx.data_ptr(),
-               L.SX_F32, _rt(), dg.data_ptr(), db.data_ptr(), _stream())
+               L.SX_F32, _rt(), dgb.data_ptr(), dbb.data_ptr(), _stream())
         return dx, dg, db
 
 
@@ -618,6 +659,7 @@ class _GroupLinear(torch.autograd.Function):
         gemm_nt(G, Wr.unsqueeze(0), out=Y, bias=bo.reshape(1, M, Fd), round_out=False)
         ctx.save_for_backward(G, Wr)
         ctx.wshape = Wo.shape
+        ctx.leaves = (Wo, bo)
         return Y
 
     @staticmethod
@@ -628,13 +670,21 @@ class _GroupLinear(torch.autograd.Function):
         dG = dW = db = None
         if ctx.needs_input_grad[0]:
             dG = gemm_nt(dY, Wr.transpose(-1, -2).unsqueeze(0), round_out=False)
+        Wo, bo = ctx.leaves
         if ctx.needs_input_grad[1]:
-            dW = gemm_nt(dY.transpose(-1, -2), G.transpose(-1, -2), reduce_z1=True, round_out=False)
-            dW = dW.view(ctx.wshape)
+            tgt = _grad_target(Wo)
+            if tgt is not None:
+                gemm_nt(dY.transpose(-1, -2), G.transpose(-1, -2), out=tgt.view(1, M, Fd, Fd), reduce_z1=True,
+                        accumulate=True, round_out=False)
+            else:
+                dW = gemm_nt(dY.transpose(-1, -2), G.transpose(-1, -2), reduce_z1=True, round_out=False)
+                dW = dW.view(ctx.wshape)
         if ctx.needs_input_grad[2]:
-            db = torch.zeros((M, Fd), device=G.device, dtype=torch.float32)
+            tgt = _grad_target(bo)
+            db = tgt if tgt is not None else torch.zeros((M * Fd,), device=G.device, dtype=torch.float32)
             L.call("sx_colsum_batched", dY.data_ptr(), B, M * N * Fd, M, N * Fd, N, Fd, Fd, db.data_ptr(), _stream())
-            db = db.view(-1)
+            if tgt is not None:
+                db = None
         return dG, dW, db
 
 
@@ -652,6 +702,7 @@ class _LnSoftAggr(torch.autograd.Function):
                bs.data_ptr(), drop_p, *_seed_args(seed), out.data_ptr(), stats.data_ptr(), wts.data_ptr(), _stream())
         ctx.save_for_backward(Y, g, b, ws, stats, wts)
         ctx.meta = (drop_p, seed, bs.shape, ws.shape)
+        ctx.leaves = (g, b, ws, bs)
         return out
 
     @staticmethod
@@ -661,15 +712,15 @@ class _LnSoftAggr(torch.autograd.Function):
         B, M, N, Fd = Y.shape
         dout = dout.contiguous()
         dY = torch.empty_like(Y)
-        dg = torch.zeros_like(g)
-        db = torch.zeros_like(g)
-        dws = torch.zeros(Fd, device=Y.device, dtype=torch.float32)
-        dbs = torch.zeros(1, device=Y.device, dtype=torch.float32)
+        dgb, dg = _sink_or_zeros(ctx.leaves[0])
+        dbb, db = _sink_or_zeros(ctx.leaves[1])
+        dwsb, dws = _sink_or_zeros(ctx.leaves[2])
+        dbsb, dbs = _sink_or_zeros(ctx.leaves[3])
         scratch = torch.empty(B * M * N, device=Y.device, dtype=torch.float32)
         L.call("sx_ln_softaggr_bwd", dout.data_ptr(), Y.data_ptr(), B, M, N, Fd, g.data_ptr(), b.data_ptr(),
-               ws.data_ptr(), drop_p, *_seed_args(seed), stats.data_ptr(), wts.data_ptr(), dY.data_ptr(), L.SX_F32, _rt(), dg.data_ptr(),
-               db.data_ptr(), dws.data_ptr(), dbs.data_ptr(), scratch.data_ptr(), _stream())
-        return dY, dg, db, dws.view(ws_shape), dbs.view(bs_shape), None, None
+               ws.data_ptr(), drop_p, *_seed_args(seed), stats.data_ptr(), wts.data_ptr(), dY.data_ptr(), L.SX_F32, _rt(), dgb.data_ptr(),
+               dbb.data_ptr(), dwsb.data_ptr(), dbsb.data_ptr(), scratch.data_ptr(), _stream())
+        return dY, dg, db, dws, dbs, None, None
 
 
 class _PosCode(torch.autograd.Function):
@@ -687,6 +738,7 @@ class _PosCode(torch.autograd.Function):
         L.call("sx_pos_lsinu_fwd", pos2d.data_ptr(), pmax.data_ptr(), R, pd, Wc.data_ptr(), bc.data_ptr(), C0,
                pe.data_ptr(), _stream())
         ctx.save_for_backward(pos2d, pmax, Wc, bc)
+        ctx.leaves = (W, b)
         return pe
 
     @staticmethod
@@ -696,10 +748,10 @@ class _PosCode(torch.autograd.Function):
         C0 = W.shape[0]
         dpe = dpe.contiguous()
         scratch = torch.empty_like(dpe)
-        dW = torch.zeros_like(W)
-        db = torch.zeros_like(b)
+        dWb, dW = _sink_or_zeros(ctx.leaves[0], like=W)
+        dbb, db = _sink_or_zeros(ctx.leaves[1], like=b)
         L.call("sx_pos_lsinu_bwd", pos2d.data_ptr(), pmax.data_ptr(), R, pd, W.data_ptr(), b.data_ptr(), C0,
-               dpe.data_ptr(), scratch.data_ptr(), dW.data_ptr(), db.data_ptr(), _stream())
+               dpe.data_ptr(), scratch.data_ptr(), dWb.data_ptr(), dbb.data_ptr(), _stream())
         return None, dW, db
 
 
@@ -719,6 +771,7 @@ class _Prologue(torch.autograd.Function):
                posw, _ptr(mask), drop_p, *_seed_args(seed), h.data_ptr(), L.SX_F32, _rt(), stats.data_ptr(), _stream())
         ctx.save_for_backward(x, g, b, pe, mask, stats)
         ctx.meta = (posw, drop_p, seed, pe_bstride)
+        ctx.leaves = (g, b)
         return h
 
     @staticmethod
@@ -729,12 +782,12 @@ class _Prologue(torch.autograd.Function):
         C0 = pe.shape[-1]
         dh = dh.contiguous()
         dx = torch.empty_like(x)
-        dg = torch.zeros_like(g)
-        db = torch.zeros_like(b)
+        dgb, dg = _sink_or_zeros(ctx.leaves[0])
+        dbb, db = _sink_or_zeros(ctx.leaves[1])
         dpe = torch.zeros_like(pe) if ctx.needs_input_grad[3] else None
         scratch = torch.empty_like(x)
         L.call("sx_prologue_bwd", dh.data_ptr(), x.data_ptr(), B, N, Cd, g.data_ptr(), b.data_ptr(), pe.data_ptr(), C0,
-               pe_bstride, posw, _ptr(mask), drop_p, *_seed_args(seed), stats.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(),
+               pe_bstride, posw, _ptr(mask), drop_p, *_seed_args(seed), stats.data_ptr(), dx.data_ptr(), dgb.data_ptr(), dbb.data_ptr(),
                _ptr(dpe), scratch.data_ptr(), _stream())
         return dx, dg, db, dpe, None, None, None, None
 

@@ -18,7 +18,8 @@ import torch.distributed as dist
 
 
 class GradBucket:
-    def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None, overlap_chunks: int = 0):
+    def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None, overlap_chunks: int = 0,
+                 direct_accumulate: bool = False):
         seen, self.params = set(), []
         for p in params:                      # tied parameters (query/key) appear once
             if p.requires_grad and id(p) not in seen:
@@ -34,6 +35,14 @@ class GradBucket:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)      # autograd accumulates in place into the bucket
             off += n
+        # direct_accumulate: the weight-gradient GEMMs of the hot path add straight into these views (ops.set_grad_sink)
+        # instead of producing a temporary that autograd adds in a second pass; needs zero() before every step, and the
+        # per-parameter hooks of the overlap mode do not fire for those parameters
+        if direct_accumulate:
+            if overlap_chunks > 1:
+                raise ValueError("GradBucket: direct_accumulate and overlap_chunks are mutually exclusive")
+            from . import ops
+            ops.set_grad_sink(True)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self._comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None

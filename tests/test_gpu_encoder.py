@@ -139,3 +139,35 @@ def test_training_mode_dropout_runs_and_is_consistent():
     b = g().clone()
     assert torch.isfinite(a).all() and not torch.equal(a, b)       # new mask on every replay
     assert g.kernel_launches > 20
+
+
+def test_direct_gradient_accumulation_equals_autograd():
+    """GradBucket(direct_accumulate=True): weight-gradient GEMMs / column sums add straight into the flat bucket (autograd
+    gets None for those inputs).  Same gradients as the stock AccumulateGrad path, twice in a row (accumulation)."""
+    from segtran_b200 import ops
+    from segtran_b200.parallel import GradBucket
+    fx = load_golden("enc3d_small")
+    enc = build_b200_encoder(fx).eval()
+    x = fx["x"].cuda()
+    pos, mask, G = fx["voxels_pos"].cuda(), fx["vmask"].cuda(), fx["G"].cuda()
+
+    def run():
+        y = enc(x, pos, mask, torch.Size(fx["grid"]))
+        (y * G).sum().backward()
+
+    run()
+    want = {k: p.grad.clone() for k, p in enc.named_parameters() if p.grad is not None}
+    for p in enc.parameters():
+        p.grad = None
+    try:
+        bucket = GradBucket(enc.parameters(), direct_accumulate=True)
+        run()
+        run()                                   # second pass accumulates on top of the first
+        for k, p in enc.named_parameters():
+            if k in want:
+                ref = 2.0 * want[k]
+                assert float((p.grad - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-9, k
+        bucket.zero()
+        assert all(float(p.grad.abs().max()) == 0.0 for p in enc.parameters())
+    finally:
+        ops.set_grad_sink(False)
