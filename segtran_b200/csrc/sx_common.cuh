@@ -191,37 +191,54 @@ __device__ __forceinline__ float round_tf32(float x) {
 }
 // erf by Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, one MUFU.RCP + one MUFU.EX2 + 7 FMA) — used in the GEMM
 // epilogue where the libdevice erff (~30 instructions) made the 4/8 epilogue warps the bottleneck.
+// Branch-free erf: erf(|x|) = 1 - 2^(-t q(t)), t = min(|x|, 3.93), q a degree-7 polynomial fitted (weighted minimax) to
+// -log2(erfc(t))/t.  Max abs error 1.2e-7 + the ex2.approx error (<= 2 ulp of a value <= 1), i.e. <= 2.5e-7 absolute —
+// three orders below the TF32 operand rounding that follows; 13 instructions, no divergence (libdevice erff takes two
+// branches inside most warps).  Checked against fp64 erf in tests/test_gpu_ops.py and in tf32x3 mode end to end.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float erf_fast(float x) {
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float y = 1.0f - p * t * __expf(-ax * ax);
+  const float t = fminf(fabsf(x), 3.93f);
+  float r = 4.5856195356464013e-05f;
+  r = fmaf(r, t, -4.4942606473341584e-04f);
+  r = fmaf(r, t, 1.5015227254480124e-03f);
+  r = fmaf(r, t, 7.559903897345066e-04f);
+  r = fmaf(r, t, -2.8238432481884956e-02f);
+  r = fmaf(r, t, 1.4847517013549805e-01f);
+  r = fmaf(r, t, 9.184176325798035e-01f);
+  r = fmaf(r, t, 1.62790846824646f);
+  const float y = 1.0f - ex2_approx(-r * t);
   return copysignf(y, x);
 }
-// forward GELU keeps libdevice erff: its ~1-ulp accuracy is part of the 1e-3 logit budget (measured: the polynomial
-// erf cost 2.6e-4 of max-rel error on the 3-layer 2-D stack); the gradient uses the fast form.
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 // d/dx of 0.5 x (1 + erf(x/sqrt2))
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   return 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
-// Counter-based dropout bits: one 64-bit hash per group of 4 consecutive elements (index >> 2), 16 bits per
-// element; keep(idx) <=> field(idx & 3) >= p16 with p16 = round(p * 65536).  Two rounds of a 32-bit avalanche
-// mixer (lowbias32) keyed by the seed: ~5 integer ops per element, so the mask can be regenerated in backward for free.
+// Counter-based dropout bits: every group of 4 consecutive elements (index >> 2) owns two independent 32-bit hash words
+// (word 0: elements 0,1; word 1: elements 2,3; 16 bits per element); keep(idx) <=> field(idx & 3) >= p16 with
+// p16 = round(p * 65536).  Each word is one lowbias32 avalanche of the group index keyed by its own multiplier and
+// seed half, so a thread that holds only two elements of a group computes only the word it needs; ~5 integer ops per
+// element, cheap enough to regenerate the mask in backward instead of storing it.
 __device__ __forceinline__ uint32_t drop_p16(float p) {
   const float v = p * 65536.f + 0.5f;
   return v >= 65535.f ? 65535u : (uint32_t)v;
 }
-__device__ __forceinline__ uint2 drop_hash(unsigned long long seed, unsigned long long idx4) {
-  uint32_t a = (uint32_t)idx4 * 0x9E3779B1u ^ (uint32_t)seed;
-  a ^= (uint32_t)(idx4 >> 32) * 0x85EBCA77u;
+__device__ __forceinline__ uint32_t drop_mul(int w) { return w ? 0x85EBCA77u : 0x9E3779B1u; }
+__device__ __forceinline__ uint32_t drop_key(unsigned long long seed, int w) {
+  return w ? ((uint32_t)(seed >> 32) ^ 0x68E31DA4u) : (uint32_t)seed;
+}
+__device__ __forceinline__ uint32_t drop_word_k(uint32_t mul, uint32_t key, unsigned long long idx4) {
+  uint32_t a = ((uint32_t)idx4 * mul) ^ key;
+  a ^= (uint32_t)(idx4 >> 32) * 0xC2B2AE3Du;
   a ^= a >> 16; a *= 0x7FEB352Du; a ^= a >> 15; a *= 0x846CA68Bu; a ^= a >> 16;
-  uint32_t b = a ^ (uint32_t)(seed >> 32) ^ 0x68E31DA4u;
-  b ^= b >> 16; b *= 0x21F0AAADu; b ^= b >> 15; b *= 0x735A2D97u; b ^= b >> 15;
-  return make_uint2(a, b);
+  return a;
+}
+__device__ __forceinline__ uint2 drop_hash(unsigned long long seed, unsigned long long idx4) {
+  return make_uint2(drop_word_k(drop_mul(0), drop_key(seed, 0), idx4), drop_word_k(drop_mul(1), drop_key(seed, 1), idx4));
 }
 __device__ __forceinline__ bool drop_keep(uint2 h, int j, uint32_t p16) {
   const uint32_t w = (j & 2) ? h.y : h.x;
@@ -229,7 +246,9 @@ __device__ __forceinline__ bool drop_keep(uint2 h, int j, uint32_t p16) {
 }
 // scalar form (any alignment)
 __device__ __forceinline__ bool drop_keep1(unsigned long long seed, unsigned long long idx, uint32_t p16) {
-  return drop_keep(drop_hash(seed, idx >> 2), (int)(idx & 3), p16);
+  const int j = (int)(idx & 3);
+  const uint32_t w = drop_word_k(drop_mul(j >> 1), drop_key(seed, j >> 1), idx >> 2);
+  return ((w >> ((j & 1) * 16)) & 0xFFFFu) >= p16;
 }
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   // valid for any sign mix: order-preserving int compare

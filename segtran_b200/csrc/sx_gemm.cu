@@ -346,25 +346,40 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float keep_scale = 1.f / (1.f - p.drop_p);
           const uint32_t p16 = sx::drop_p16(p.drop_p);
           const unsigned long long dseed = p.drop_seed + (p.drop_seed_dev ? *p.drop_seed_dev : 0ull);
+          if (((p.ldc | zoff) & 3) == 0) {
+            // rows start on a 4-element hash group: this thread's pair is always elements (tc&2, tc&2 + 1) of its
+            // group, i.e. one 32-bit word per pair with a per-thread constant multiplier / key
+            const int w = (tc >> 1) & 1;
+            const uint32_t mul = sx::drop_mul(w), key = sx::drop_key(dseed, w);
 #pragma unroll
-          for (int P = 0; P < 2; ++P)
+            for (int P = 0; P < 2; ++P)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const long long rbase = zoff + (long long)(row0 + 16 * P + 8 * h + tr) * p.ldc;
+              for (int h = 0; h < 2; ++h) {
+                const unsigned long long g0 =
+                    (unsigned long long)((zoff + (long long)(row0 + 16 * P + 8 * h + tr) * p.ldc + col0 + tc) >> 2);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const unsigned long long e0 = (unsigned long long)(rbase + col0 + 8 * j + tc);
-                const uint2 hsh = sx::drop_hash(dseed, e0 >> 2);
-                const int i0 = 16 * P + 4 * j + 2 * h;
-                if ((e0 & 1ull) == 0) {         // the pair lies inside one 4-element hash group
-                  f[i0] = sx::drop_keep(hsh, (int)(e0 & 3), p16) ? f[i0] * keep_scale : 0.f;
-                  f[i0 + 1] = sx::drop_keep(hsh, (int)(e0 & 3) + 1, p16) ? f[i0 + 1] * keep_scale : 0.f;
-                } else {
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t bits = sx::drop_word_k(mul, key, g0 + 2 * j);
+                  const int i0 = 16 * P + 4 * j + 2 * h;
+                  f[i0] = (bits & 0xFFFFu) >= p16 ? f[i0] * keep_scale : 0.f;
+                  f[i0 + 1] = (bits >> 16) >= p16 ? f[i0 + 1] * keep_scale : 0.f;
+                }
+              }
+          } else {
+#pragma unroll
+            for (int P = 0; P < 2; ++P)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const long long rbase = zoff + (long long)(row0 + 16 * P + 8 * h + tr) * p.ldc;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const unsigned long long e0 = (unsigned long long)(rbase + col0 + 8 * j + tc);
+                  const int i0 = 16 * P + 4 * j + 2 * h;
                   f[i0] = sx::drop_keep1(dseed, e0, p16) ? f[i0] * keep_scale : 0.f;
                   f[i0 + 1] = sx::drop_keep1(dseed, e0 + 1, p16) ? f[i0 + 1] * keep_scale : 0.f;
                 }
               }
-            }
+          }
         }
         if (p.round_tf32 && !p.c_bf16) {
 #pragma unroll

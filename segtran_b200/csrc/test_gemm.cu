@@ -197,8 +197,52 @@ static void perf(int op, int amaj, int bmaj, int M, int N, int K, int Z) {
   cudaFree(dA); cudaFree(dB); cudaFree(dC);
 }
 
+__global__ void fill_rand_kernel(float* p, size_t n, unsigned seed, float scale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned h = (unsigned)i * 2654435761u + seed;
+    h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12; h *= 0x297a2d39u; h ^= h >> 15;
+    p[i] = ((int)(h >> 8) - (1 << 23)) * (scale / (1 << 23));
+  }
+}
+
+// epilogue cost decomposition on the fused P.V' shape of the cfg-4 step: 16 x (2744 x 1024 x 1024), A K-major, B MN-major
+static void perf_epi(const char* name, int bias, int pre, int gelu, float drop, int rnd) {
+  const int M = 2744, N = 1024, K = 1024, Z = 16;
+  float *dA, *dB, *dC, *dP = nullptr, *dbias;
+  cudaMalloc(&dA, (size_t)M * K * Z * 4); cudaMalloc(&dB, (size_t)N * K * Z * 4); cudaMalloc(&dC, (size_t)M * N * Z * 4);
+  cudaMalloc(&dbias, N * 4);
+  if (pre) cudaMalloc(&dP, (size_t)M * N * Z * 4);
+  fill_rand_kernel<<<1024, 256>>>(dA, (size_t)M * K * Z, 1u, 1.0f / 32);        // softmax-like magnitudes
+  fill_rand_kernel<<<1024, 256>>>(dB, (size_t)N * K * Z, 2u, 2.0f);
+  fill_rand_kernel<<<4, 256>>>(dbias, N, 3u, 0.1f);
+  sx_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.op_dtype = SX_OP_TF32; g.M = M; g.N = N; g.K = K; g.Z0 = Z; g.Z1 = 1;
+  g.A.ptr = dA; g.A.major = SX_MAJOR_K; g.A.ld = K; g.A.stride_z0 = (long long)M * K;
+  g.B.ptr = dB; g.B.major = SX_MAJOR_MN; g.B.ld = N; g.B.stride_z0 = (long long)N * K;
+  g.C = dC; g.c_dtype = SX_F32; g.ldc = N; g.c_stride_z0 = (long long)M * N; g.alpha = 1.f; g.split_k = 1;
+  if (bias) { g.bias = dbias; g.bias_mode = SX_BIAS_N; }
+  g.preact = dP; g.act = gelu ? SX_ACT_GELU : SX_ACT_NONE; g.drop_p = drop; g.drop_seed = 77; g.round_tf32 = rnd;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 3; ++i) sx_gemm(&g, nullptr);
+  cudaDeviceSynchronize();
+  const int iters = 20;
+  cudaEventRecord(e0);
+  for (int i = 0; i < iters; ++i) sx_gemm(&g, nullptr);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms /= iters;
+  printf("EPI %-28s : %.1f us  %.1f TFLOP/s  (%s)\n", name, ms * 1e3, 2.0 * M * N * K * Z / (ms * 1e-3) / 1e12,
+         cudaGetErrorString(cudaGetLastError()));
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dbias);
+  if (dP) cudaFree(dP);
+}
+
 int main(int argc, char** argv) {
-  bool do_perf = false, ksweep = false;
+  bool do_perf = false, ksweep = false, episweep = false;
   std::string only;
   for (int i = 1; i < argc; ++i) {
     char* eq = strchr(argv[i], '=');
@@ -206,6 +250,7 @@ int main(int argc, char** argv) {
     std::string k(argv[i], eq - argv[i]);
     if (k == "perf") { do_perf = atoi(eq + 1) != 0; continue; }
     if (k == "ksweep") { ksweep = atoi(eq + 1) != 0; continue; }
+    if (k == "episweep") { episweep = atoi(eq + 1) != 0; continue; }
     if (k == "only") { only = eq + 1; continue; }
     if (sx_gemm_debug_set(k.c_str(), atoll(eq + 1)) != 0) { printf("bad knob %s\n", k.c_str()); return 3; }
     printf("knob %s=%lld\n", k.c_str(), atoll(eq + 1));
@@ -253,6 +298,17 @@ int main(int argc, char** argv) {
     if (r == 2) { printf("aborting after launch failure (context likely poisoned)\n"); break; }
   }
   printf("SUMMARY %d/%d cases passed\n", ran - fails, ran);
+  if (episweep) {
+    perf_epi("plain", 0, 0, 0, 0.f, 0);
+    perf_epi("round", 0, 0, 0, 0.f, 1);
+    perf_epi("bias+round", 1, 0, 0, 0.f, 1);
+    perf_epi("bias+round+preact", 1, 1, 0, 0.f, 1);
+    perf_epi("bias+round+gelu", 1, 0, 1, 0.f, 1);
+    perf_epi("bias+round+dropout", 1, 0, 0, 0.2f, 1);
+    perf_epi("bias+round+gelu+dropout", 1, 0, 1, 0.2f, 1);
+    perf_epi("all (preact+gelu+dropout)", 1, 1, 1, 0.2f, 1);
+    return 0;
+  }
   if (ksweep) {
     const int Ks[] = {128, 256, 512, 1024, 2048, 4096};
     for (int kk : Ks) perf(T, K_, K_, 128 * 74, 256 * 20, kk, 1);      // 1480 tiles = exactly 10 waves of 148

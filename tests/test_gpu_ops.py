@@ -72,6 +72,19 @@ def test_gemm_nt_tf32x3_recovers_fp32_products():
     assert e1 > 1e-5          # the single-pass mode on un-rounded operands is visibly TF32
 
 
+def test_epilogue_gelu_matches_fp64_erf():
+    """The branch-free erf of the GEMM epilogue (sx_common.cuh erf_fast): |gelu - fp64 gelu| <= 4e-7 * max(1, |x|) over
+    [-8, 8] — three orders below the TF32 operand rounding.  x is fed through an exact identity GEMM (TF32-exact inputs)."""
+    from segtran_b200 import ops
+    x = tf32(torch.linspace(-8, 8, 128 * 1024, device="cuda"))
+    a = torch.zeros(x.numel(), 4, device="cuda")
+    a[:, 0] = x
+    y = ops.gemm_nt(a, torch.eye(4, device="cuda"), gelu=True, round_out=False)[0, 0, :, 0]
+    ref = torch.nn.functional.gelu(x.double())
+    err = (y.double() - ref).abs() / x.double().abs().clamp_min(1.0)
+    assert float(err.max()) < 4e-7, float(err.max())
+
+
 def test_linear_fwd_bwd_gelu():
     from segtran_b200 import ops
     x = torch.randn(5, 37, 96, device="cuda", requires_grad=True)
