@@ -37,7 +37,8 @@ enum { SX_OP_TF32 = 0, SX_OP_BF16 = 1 };
 /* operand majorness: K-major = reduction dim contiguous; MN-major = row/col dim contiguous */
 enum { SX_MAJOR_K = 0, SX_MAJOR_MN = 1 };
 enum { SX_BIAS_NONE = 0, SX_BIAS_N = 1, SX_BIAS_M = 2 };
-enum { SX_ACT_NONE = 0, SX_ACT_GELU = 1 };
+enum { SX_ACT_NONE = 0, SX_ACT_GELU = 1,
+       SX_ACT_GELU_BWD = 2 /* C = dropmask * (alpha A.B^T) * gelu'(preact): `preact` is an INPUT in C's layout */ };
 
 int sx_version(void);
 const char* sx_last_error(void);
@@ -189,6 +190,9 @@ int sx_head_contract_bwd_weight(const float* dL, const float* curr, int32_t B, i
 /* class scores of the fused tokens, exact fp32: out[b,k,n] = sum_f W[k,f] vf[b,n,f]   (Wc . vfeat_fused) */
 int sx_token_scores(const float* vf, const float* W, int32_t B, int32_t N, int32_t F, int32_t K, float* out,
                     void* stream);
+/* and its data gradient: dvf[b,n,f] = sum_k dt[b,k,n] W[k,f]   (F % 4 == 0) */
+int sx_token_scores_bwd(const float* dt, const float* W, int32_t B, int32_t N, int32_t F, int32_t K, float* dvf,
+                        void* stream);
 /* 1-D linear resampling (align_corners=False) of x viewed as [outer, Lin, inner] -> [outer, Lout, inner];
  * F.interpolate(mode='bilinear'|'trilinear') == one pass per axis. */
 int sx_resize_axis_fwd(const float* x, int64_t outer, int32_t Lin, int32_t Lout, int64_t inner, float* y,

@@ -15,7 +15,7 @@ SX_F32, SX_BF16 = 0, 1
 SX_OP_TF32, SX_OP_BF16 = 0, 1
 SX_MAJOR_K, SX_MAJOR_MN = 0, 1
 SX_BIAS_NONE, SX_BIAS_N, SX_BIAS_M = 0, 1, 2
-SX_ACT_NONE, SX_ACT_GELU = 0, 1
+SX_ACT_NONE, SX_ACT_GELU, SX_ACT_GELU_BWD = 0, 1, 2
 
 
 class SxError(RuntimeError):
@@ -69,6 +69,7 @@ _PROTOS = {
     "sx_head_contract_bwd_data": [_P, _P, _I, _I, _L, _I, _P, _P],
     "sx_head_contract_bwd_weight": [_P, _P, _I, _I, _L, _I, _P, _P],
     "sx_token_scores": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "sx_token_scores_bwd": [_P, _P, _I, _I, _I, _I, _P, _P],
     "sx_resize_axis_fwd": [_P, _L, _I, _I, _L, _P, _I, _P],
     "sx_resize_axis_bwd": [_P, _L, _I, _I, _L, _P, _P],
     "sx_sgemm_small": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _L, _L, _L, _F, _I, _P],

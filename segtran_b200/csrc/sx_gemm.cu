@@ -269,6 +269,29 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     };
 
+    // fp32 tensor in C's layout -> the same fragment distribution (out-of-range elements read as 0)
+    auto load_frag = [&](const float* base, float (&g)[32], long long zoff, int row0, int col0) {
+#pragma unroll
+      for (int P = 0; P < 2; ++P)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int grow = row0 + 16 * P + 8 * h + tr;
+          const float* ar = base + zoff + (long long)(grow < p.M ? grow : 0) * p.ldc;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = col0 + 8 * j + tc;
+            const int i0 = 16 * P + 4 * j + 2 * h;
+            if (grow < p.M && col + 1 < p.N && p.c_vec_ok) {
+              const float2 v = *reinterpret_cast<const float2*>(ar + col);
+              g[i0] = v.x; g[i0 + 1] = v.y;
+            } else {
+              g[i0] = (grow < p.M && col < p.N) ? ar[col] : 0.f;
+              g[i0 + 1] = (grow < p.M && col + 1 < p.N) ? ar[col + 1] : 0.f;
+            }
+          }
+        }
+    };
+
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int z0, z1, mb, nb, ks;
       decode(t, z0, z1, mb, nb, ks);
@@ -306,22 +329,10 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           f[16 + i] = __uint_as_float(vb[i]) * p.alpha + bias_m[2 + ((i >> 1) & 1)];
         }
         if (p.addend) {
+          float g[32];
+          load_frag(p.addend, g, zoff, row0, col0);
 #pragma unroll
-          for (int P = 0; P < 2; ++P)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int grow = row0 + 16 * P + 8 * h + tr;
-              if (grow < p.M) {
-                const float* ar = p.addend + zoff + (long long)grow * p.ldc;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                  for (int e = 0; e < 2; ++e) {
-                    const int col = col0 + 8 * j + tc + e;
-                    if (col < p.N) f[16 * P + 4 * j + 2 * h + e] += ar[col];
-                  }
-              }
-            }
+          for (int i = 0; i < 32; ++i) f[i] += g[i];
         }
         if (add_bias && p.bias_mode == SX_BIAS_N) {
 #pragma unroll
@@ -337,10 +348,17 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
           }
         }
-        if (p.preact) store_frag(p.preact, f, zoff, row0, col0, false);
-        if (p.act == SX_ACT_GELU) {
+        if (p.act == SX_ACT_GELU_BWD) {         // C = mask * acc * gelu'(h), h = the forward pre-activation (read-only)
+          float g[32];
+          load_frag(reinterpret_cast<const float*>(p.preact), g, zoff, row0, col0);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = sx::gelu_erf(f[i]);
+          for (int i = 0; i < 32; ++i) f[i] *= sx::gelu_erf_grad(g[i]);
+        } else {
+          if (p.preact) store_frag(p.preact, f, zoff, row0, col0, false);
+          if (p.act == SX_ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = sx::gelu_erf(f[i]);
+          }
         }
         if (p.drop_p > 0.f) {
           const float keep_scale = 1.f / (1.f - p.drop_p);
@@ -566,11 +584,14 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
   p.ldc = a->ldc; p.c_sz0 = a->c_stride_z0; p.c_sz1 = a->c_stride_z1;
   // the epilogue stores column pairs (8 bytes fp32 / 4 bytes bf16): pairs must stay naturally aligned
   p.c_vec_ok = ((reinterpret_cast<uintptr_t>(a->C) & 7) == 0) && (a->ldc % 2 == 0) && (a->c_stride_z0 % 2 == 0) &&
-               (a->c_stride_z1 % 2 == 0) && (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 7) == 0);
+               (a->c_stride_z1 % 2 == 0) && (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 7) == 0) &&
+               (!a->addend || (reinterpret_cast<uintptr_t>(a->addend) & 7) == 0);
   p.alpha = a->alpha; p.bias_mode = a->bias ? a->bias_mode : SX_BIAS_NONE; p.bias = a->bias;
   p.bias_sz0 = a->bias_stride_z0; p.bias_sz1 = a->bias_stride_z1;
   p.act = a->act; p.accumulate = a->accumulate; p.preact = a->preact; p.amax = a->amax;
   p.addend = a->addend;
+  SX_REQUIRE(a->act != SX_ACT_GELU_BWD || (a->preact && a->c_dtype == SX_F32 && p.split_k == 1 && !a->accumulate),
+             "sx_gemm: SX_ACT_GELU_BWD needs the fp32 pre-activation in `preact`, fp32 C, split_k=1, accumulate=0");
   SX_REQUIRE(!a->addend || (p.split_k == 1 && !a->accumulate && a->c_dtype == SX_F32), "sx_gemm: addend needs split_k=1, accumulate=0, fp32 C");
   p.drop_p = a->drop_p; p.drop_seed = a->drop_seed;
   p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(a->drop_seed_dev);

@@ -359,6 +359,7 @@ __global__ void resize_last_x2_bwd_kernel(const float* __restrict__ dy, unsigned
 }
 
 // ---- class scores of the fused tokens, exact fp32: out[b,k,n] = sum_f W[k,f] vf[b,n,f]; one warp per token ----
+template <bool V4>
 __global__ void token_scores_kernel(const float* __restrict__ vf, const float* __restrict__ W, long long T, int N,
                                     int F, int K, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
@@ -368,11 +369,24 @@ __global__ void token_scores_kernel(const float* __restrict__ vf, const float* _
   float acc[MAXK];
 #pragma unroll
   for (int k = 0; k < MAXK; ++k) acc[k] = 0.f;
-  for (int f = lane; f < F; f += 32) {
-    const float xv = x[f];
+  if (V4) {                                 // F % 4 == 0, 16-byte aligned rows: 4 x 512 B of the token row in flight
+#pragma unroll 4
+    for (int f = lane * 4; f < F; f += 128) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + f);
 #pragma unroll
-    for (int k = 0; k < MAXK; ++k)
-      if (k < K) acc[k] = fmaf(xv, __ldg(W + (long long)k * F + f), acc[k]);
+      for (int k = 0; k < MAXK; ++k)
+        if (k < K) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)k * F + f));
+          acc[k] = fmaf(xv.x, w.x, fmaf(xv.y, w.y, fmaf(xv.z, w.z, fmaf(xv.w, w.w, acc[k]))));
+        }
+    }
+  } else {
+    for (int f = lane; f < F; f += 32) {
+      const float xv = x[f];
+#pragma unroll
+      for (int k = 0; k < MAXK; ++k)
+        if (k < K) acc[k] = fmaf(xv, __ldg(W + (long long)k * F + f), acc[k]);
+    }
   }
   const long long b = t / N, n = t % N;
 #pragma unroll
@@ -381,6 +395,27 @@ __global__ void token_scores_kernel(const float* __restrict__ vf, const float* _
       const float s = sx::warp_sum(acc[k]);
       if (lane == 0) out[(b * K + k) * N + n] = s;
     }
+}
+
+// ---- its data gradient: dvf[b,n,f] = sum_k dt[b,k,n] W[k,f]; one thread per 4 channels, writes coalesced ----
+__global__ void token_scores_bwd_kernel(const float* __restrict__ dt, const float* __restrict__ W, long long T, int N,
+                                        int F, int K, float* __restrict__ dvf) {
+  const int F4 = F >> 2;
+  const long long total = T * F4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / F4;
+    const int f = (int)(i - t * F4) * 4;
+    const long long b = t / N, n = t - b * N;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k)
+      if (k < K) {
+        const float d = __ldg(dt + (b * K + k) * N + n);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)k * F + f));
+        acc.x = fmaf(d, w.x, acc.x); acc.y = fmaf(d, w.y, acc.y); acc.z = fmaf(d, w.z, acc.z); acc.w = fmaf(d, w.w, acc.w);
+      }
+    *reinterpret_cast<float4*>(dvf + t * F + f) = acc;
+  }
 }
 
 // ---- tiny strided fp32 GEMM: C[z][m][n] (+)= alpha * sum_k A[z](m,k) B[z](k,n) ----
@@ -424,7 +459,8 @@ __global__ void sgemm_small_warp_kernel(const float* __restrict__ A, const float
   const float* a = A + z * saz + (long long)m * sam;
   const float* b = B + z * sbz + (long long)n * sbn;
   float acc = 0.f;
-  for (int k = lane; k < K; k += 32) acc = fmaf(a[(long long)k * sak], b[(long long)k * sbk], acc);
+#pragma unroll 8
+  for (int k = lane; k < K; k += 32) acc = fmaf(a[(long long)k * sak], b[(long long)k * sbk], acc);   // 16 loads in flight
   acc = sx::warp_sum(acc);
   if (lane == 0) {
     float* c = C + z * scz + (long long)m * scm + (long long)n * scn;
@@ -575,7 +611,23 @@ extern "C" int sx_token_scores(const float* vf, const float* W, int32_t B, int32
                                void* stream) {
   SX_REQUIRE(K >= 1 && K <= MAXK, "sx_token_scores: num_classes %d not in 1..%d", K, MAXK);
   const long long T = (long long)B * N;
-  token_scores_kernel<<<sx_ceil_div(T, 8), 256, 0, ST(stream)>>>(vf, W, T, N, F, K, out);
+  if (F % 4 == 0 && (reinterpret_cast<uintptr_t>(vf) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0)
+    token_scores_kernel<true><<<sx_ceil_div(T, 8), 256, 0, ST(stream)>>>(vf, W, T, N, F, K, out);
+  else
+    token_scores_kernel<false><<<sx_ceil_div(T, 8), 256, 0, ST(stream)>>>(vf, W, T, N, F, K, out);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_token_scores_bwd(const float* dt, const float* W, int32_t B, int32_t N, int32_t F, int32_t K, float* dvf,
+                                   void* stream) {
+  SX_REQUIRE(dt && W && dvf && B >= 1 && N >= 1 && F >= 1, "sx_token_scores_bwd: bad arguments");
+  SX_REQUIRE(K >= 1 && K <= MAXK, "sx_token_scores_bwd: num_classes %d not in 1..%d", K, MAXK);
+  SX_REQUIRE(F % 4 == 0 && (reinterpret_cast<uintptr_t>(dvf) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+             "sx_token_scores_bwd: F must be a multiple of 4 and W/dvf 16-byte aligned");
+  const long long T = (long long)B * N, total = T * (F / 4);
+  const int grid = (int)std::min<long long>(sx_ceil_div(total, 256), 148LL * 16);
+  token_scores_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(dt, W, T, N, F, K, dvf);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

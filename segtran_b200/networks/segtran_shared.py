@@ -241,9 +241,11 @@ class ExpandedFeatTrans(nn.Module):
             B, U2 = input_feat.shape[0], input_feat.shape[1]
             vp = ops.linear(v.view(B, U2, M, self.feat_dim), mid.shared_linear.weight).view(B, U2, M * self.feat_dim)
             p = mid.dropout.p if self.training else 0.0
-            g = ops.attn_pv_gelu(attention_probs, vp, M, mid.shared_linear.bias, p,
-                                 ops.new_dropout_seed(vp.device) if p > 0 else 0)
-            y = self.output(g, None)
+            # ... and MMPrivateOutput's grouped Linear rides in the same autograd node (its backward fuses GELU' and
+            # the dropout mask into the dG GEMM epilogue)
+            gl = self.output.group_linear
+            y = ops.attn_pv_gelu_group_linear(attention_probs, vp, M, mid.shared_linear.bias, p,
+                                              ops.new_dropout_seed(vp.device) if p > 0 else 0, gl.weight, gl.bias)
         else:
             u = ops.attn_pv(attention_probs, v, M)
             g = self.intermediate(u)

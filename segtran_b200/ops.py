@@ -185,7 +185,8 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
                bias: Optional[torch.Tensor] = None, bias_mode: int = L.SX_BIAS_N, gelu: bool = False,
                preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
                amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
-               reduce_z1: bool = False, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+               reduce_z1: bool = False, addend: Optional[torch.Tensor] = None,
+               gelu_bwd: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a [..., M, K], b [..., N, K] (strided fp32 views; either dim may be the contiguous one) ->
     out [z1, z0, M, N] fp32.  With reduce_z1 the z1 batch dim is summed into one output (atomic accumulate)."""
     _req_cuda(a, b, out, bias, preact, amax)
@@ -203,7 +204,7 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
             raise L.SxError("gemm_nt: batch dims do not broadcast")
     oz1 = 1 if reduce_z1 else Z1
     fresh = out is None
-    linear_epi = (not gelu) and preact is None and drop_p == 0.0 and amax is None
+    linear_epi = (not gelu) and preact is None and drop_p == 0.0 and amax is None and gelu_bwd is None
     if split_k is None:
         split_k = _pick_split_k(M, N, K, Z0 * Z1) if (linear_epi and (fresh or accumulate or reduce_z1)) else 1
     if fresh:
@@ -233,6 +234,11 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
         g.bias_stride_z0 = b4b.stride(1) if b4b.shape[1] > 1 else 0
         g.bias_stride_z1 = b4b.stride(0) if b4b.shape[0] > 1 else 0
     g.act = L.SX_ACT_GELU if gelu else L.SX_ACT_NONE
+    if gelu_bwd is not None:                 # C = dropmask * (A.B^T) * gelu'(h): h (C's layout) goes in through `preact`
+        if gelu or preact is not None or tuple(gelu_bwd.shape[-2:]) != (M, N) or gelu_bwd.stride() != out.stride():
+            raise L.SxError("gemm_nt: gelu_bwd needs the pre-activation in the output's layout and no other activation")
+        g.act = L.SX_ACT_GELU_BWD
+        g.preact = gelu_bwd.data_ptr()
     g.split_k = split_k
     g.accumulate = 1 if (accumulate or reduce_z1 or split_k > 1) else 0
     if preact is not None:
@@ -264,13 +270,13 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = N
             bias: Optional[torch.Tensor] = None, bias_mode: int = L.SX_BIAS_N, gelu: bool = False,
             preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
             amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
-            reduce_z1: bool = False) -> torch.Tensor:
+            reduce_z1: bool = False, gelu_bwd: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C[..., m, n] = epilogue(alpha * sum_k a[..., m, k] b[..., n, k]) on the tcgen05 GEMM.  In the default
     precision this is one launch; in 'tf32x3' it is three passes on the hi/lo operand splits."""
     if _PRECISION == "tf32":
         return _gemm_nt_1(a, b, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
                           accumulate=accumulate, split_k=split_k, amax=amax, drop_p=drop_p, seed=seed,
-                          round_out=round_out, reduce_z1=reduce_z1)
+                          round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd)
     _req_cuda(a, b)
     ah, al = _tf32_split(a)
     bh, bl = _tf32_split(b)
@@ -289,7 +295,7 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = N
     _gemm_nt_1(al, bh, out=part, alpha=alpha, split_k=1, round_out=False)
     _gemm_nt_1(ah, bl, out=part, alpha=alpha, split_k=1, round_out=False, addend=part)
     return _gemm_nt_1(ah, bh, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
-                      split_k=1, amax=amax, drop_p=drop_p, seed=seed, round_out=False, addend=part)
+                      split_k=1, amax=amax, drop_p=drop_p, seed=seed, round_out=False, addend=part, gelu_bwd=gelu_bwd)
 
 
 def _pad4(n: int) -> int:
@@ -616,6 +622,72 @@ class _AttnPVGelu(torch.autograd.Function):
 
 def attn_pv_gelu(P, v, M, bias, drop_p=0.0, seed=0):
     return _AttnPVGelu.apply(P, v, M, bias, drop_p, seed)
+
+
+class _AttnPVGeluGroupLinear(torch.autograd.Function):
+    """Y[b,m] = dropout(gelu(P[b,m] V'[b,:,m] + bm)) Wo[m]^T + bo[m]: _AttnPVGelu followed by _GroupLinear as ONE autograd
+    node, so that backward can fuse gelu'(h) * dropout mask into the epilogue of the dG = dY Wo GEMM (SX_ACT_GELU_BWD)
+    instead of writing dG, re-reading it with the pre-activation and writing dH in a separate pass."""
+
+    @staticmethod
+    def forward(ctx, P, v, M, bm, drop_p, seed, Wo, bo):
+        B, _, U1, U2 = P.shape
+        Fd = v.shape[-1] // M
+        P = _rowpad(P)
+        vv = v.view(B, U2, M, Fd).permute(0, 2, 3, 1)
+        G = torch.empty((B, M, U1, Fd), device=P.device, dtype=torch.float32)
+        H = torch.empty_like(G)
+        gemm_nt(P, vv, out=G, bias=bm, gelu=True, preact=H, drop_p=drop_p, seed=seed)
+        Wr = round_tf32(Wo.reshape(M, Fd, Fd))
+        Y = torch.empty_like(G)
+        gemm_nt(G, Wr.unsqueeze(0), out=Y, bias=bo.reshape(1, M, Fd), round_out=False)
+        ctx.save_for_backward(P, v, H, G, Wr)
+        ctx.meta = (M, Fd, drop_p, bm is not None, Wo.shape)
+        ctx.seed = seed
+        ctx.leaves = (bm, Wo, bo)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        P, v, H, G, Wr = ctx.saved_tensors
+        M, Fd, drop_p, has_bm, wshape = ctx.meta
+        bm, Wo, bo = ctx.leaves
+        B, _, U1, U2 = P.shape
+        dY = dY.contiguous()
+        dP = dv = dbm = dW = dbo = None
+        # dH = mask * (dY Wo) * gelu'(H), TF32-rounded for the two GEMMs that consume it
+        dH = torch.empty_like(H)
+        gemm_nt(dY, Wr.transpose(-1, -2).unsqueeze(0), out=dH, gelu_bwd=H, drop_p=drop_p, seed=ctx.seed)
+        if ctx.needs_input_grad[6]:
+            tgt = _grad_target(Wo)
+            if tgt is not None:
+                gemm_nt(dY.transpose(-1, -2), G.transpose(-1, -2), out=tgt.view(1, M, Fd, Fd), reduce_z1=True,
+                        accumulate=True, round_out=False)
+            else:
+                dW = gemm_nt(dY.transpose(-1, -2), G.transpose(-1, -2), reduce_z1=True, round_out=False).view(wshape)
+        if ctx.needs_input_grad[7]:
+            tgt = _grad_target(bo)
+            dbo_buf = tgt if tgt is not None else torch.zeros((M * Fd,), device=G.device, dtype=torch.float32)
+            L.call("sx_colsum_batched", dY.data_ptr(), B, M * U1 * Fd, M, U1 * Fd, U1, Fd, Fd, dbo_buf.data_ptr(), _stream())
+            dbo = None if tgt is not None else dbo_buf
+        if ctx.needs_input_grad[0]:
+            dP = _rowpad_empty((B, M, U1, U2), P.device)
+            gemm_nt(dH, v.view(B, U2, M, Fd).permute(0, 2, 1, 3), out=dP, round_out=False)
+        if ctx.needs_input_grad[1]:
+            dv = torch.empty_like(v)
+            gemm_nt(P.transpose(-1, -2), dH.transpose(-1, -2), out=dv.view(B, U2, M, Fd).permute(0, 2, 1, 3),
+                    round_out=False)
+        if has_bm and ctx.needs_input_grad[3]:
+            tgt = _grad_target(bm)
+            if tgt is not None:
+                colsum(dH.view(-1, Fd), out=tgt)
+            else:
+                dbm = colsum(dH.view(-1, Fd))
+        return dP, dv, None, dbm, None, None, dW, dbo
+
+
+def attn_pv_gelu_group_linear(P, v, M, bm, drop_p, seed, Wo, bo):
+    return _AttnPVGeluGroupLinear.apply(P, v, M, bm, drop_p, seed, Wo, bo)
 
 
 class _LayerNorm(torch.autograd.Function):
@@ -1029,7 +1101,11 @@ class _TokenClassScores(torch.autograd.Function):
         K = Wc.shape[0]
         dt = dt.contiguous()
         # dvf[b,n,f] = sum_k dt[b,k,n] Wc[k,f]      (K = num_classes: CUDA-core product, coalesced over f)
-        dvf = _sgemm(dt, Wc, N, Fd, K, (1, N), (Fd, 1), Z=B, zs=(K * N, 0, N * Fd))
+        if Fd % 4 == 0:
+            dvf = torch.empty_like(vf)
+            L.call("sx_token_scores_bwd", dt.data_ptr(), Wc.data_ptr(), B, N, Fd, K, dvf.data_ptr(), _stream())
+        else:
+            dvf = _sgemm(dt, Wc, N, Fd, K, (1, N), (Fd, 1), Z=B, zs=(K * N, 0, N * Fd))
         # dWc[k,f] = sum_{b,n} dt[b,k,n] vf[b,n,f]  (tensor cores, reduced over the batch)
         if N % 4 == 0:
             dWc = gemm_nt(dt.view(B, 1, K, N), vf.transpose(1, 2).unsqueeze(1), reduce_z1=True, round_out=False)

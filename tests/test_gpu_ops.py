@@ -85,6 +85,30 @@ def test_epilogue_gelu_matches_fp64_erf():
     assert float(err.max()) < 4e-7, float(err.max())
 
 
+def test_gemm_gelu_bwd_epilogue_equals_separate_pass():
+    """SX_ACT_GELU_BWD: C = dropmask * (A B^T) * gelu'(h) in the GEMM epilogue == plain GEMM followed by sx_gelu_bwd with
+    the same seed (bit-for-bit the same mask), and == the analytic fp64 expression when dropout is off."""
+    import segtran_b200._lib as L
+    from segtran_b200 import ops
+    a = tf32(torch.randn(3, 200, 96, device="cuda"))
+    b = tf32(torch.randn(3, 136, 96, device="cuda"))
+    h = torch.randn(1, 3, 200, 136, device="cuda") * 2
+    fused = ops.gemm_nt(a, b, gelu_bwd=h, round_out=False)
+    hd = h.double()
+    gp = 0.5 * (1 + torch.erf(hd / 2 ** 0.5)) + hd * torch.exp(-0.5 * hd * hd) / (2 * torch.pi) ** 0.5
+    close(fused.double(), (a.double() @ b.double().transpose(-1, -2)).unsqueeze(0) * gp, 2e-6)
+    seed = ops.new_dropout_seed(a.device)
+    fused = ops.gemm_nt(a, b, gelu_bwd=h, drop_p=0.3, seed=seed, round_out=False)
+    plain = ops.gemm_nt(a, b, round_out=False)
+    sep = torch.empty_like(plain)
+    L.call("sx_gelu_bwd", plain.data_ptr(), h.data_ptr(), L.SX_F32, plain.numel(), 0.3, 0, seed.data_ptr(),
+           sep.data_ptr(), L.SX_F32, 0, torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(fused == 0, sep == 0)
+    close(fused.double(), sep.double(), 1e-6)
+    frac = float((fused == 0).float().mean())
+    assert abs(frac - 0.3) < 0.01
+
+
 def test_linear_fwd_bwd_gelu():
     from segtran_b200 import ops
     x = torch.randn(5, 37, 96, device="cuda", requires_grad=True)
