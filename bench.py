@@ -34,6 +34,8 @@ sys.path.insert(0, ROOT)
 CFG = dict(B=4, S=112, C0=1024, Cf=832, grid=(14, 14, 14), sp1=(56, 56, 56), classes=4, attractors=1024, modes=4,
            dropout=0.2)
 METRIC = "voxels/sec fwd+bwd Segtran3d BraTS 112^3 bs=4 hot path"
+# training-step settings of the reference for --net segtran on BraTS (train3d.py:211-212, :223, :61, :73)
+TRAIN = dict(lr=2e-4, decay=1e-4, grad_clip=0.1, dice_w=0.5, bce_weight=[0., 3., 1., 1.75], warmup=0.05, t_total=10000)
 
 
 def model_args(device, dropout):
@@ -119,22 +121,32 @@ def oracle_step_factory(sample_B=1, crop=1):
     p["out_fpn_bridgeconv3d.bias"] = torch.zeros(C0).requires_grad_()
     p["out_conv3d.weight"] = (torch.randn(K, C0, 1, 1, 1) * 0.02).requires_grad_()
     p["out_conv3d.bias"] = torch.zeros(K).requires_grad_()
+    from oracle import train_oracle as T
     feat = torch.randn(sample_B, C0, *g, requires_grad=True)
     curr = torch.randn(sample_B, Cf, *sp1, requires_grad=True)
-    G = torch.randn(sample_B, K, S, S, S) / (sample_B * K * S ** 3)
+    Y = (torch.rand(sample_B, K, S, S, S) > 0.7).float()                   # synthetic n-hot masks
+    pw, cw = T.normalised_bce_weight(TRAIN["bce_weight"], K), T.default_class_weights(K)
     vmask = torch.ones(sample_B, g[0] * g[1] * g[2])
-    leaves = [v for v in p.values()] + [feat, curr]
+    names = list(p.keys())
+    params = [p[k] for k in names]
+    leaves = params + [feat, curr]
+    state = {}
 
     def step():
         for v in leaves:
             v.grad = None
         y = O.hot_path_3d(p, feat, curr, vmask, (S, S, S), [C0, C0], M, 2, hid_drop=CFG["dropout"],
                           att_drop=CFG["dropout"], training=True)
-        loss = (y * G).sum()
+        loss, _, _ = T.seg_loss(y, Y, pw, cw, TRAIN["dice_w"])             # train3d.py:731-756
         loss.backward()
+        with torch.no_grad():                                              # train3d.py:760-762
+            gs = [v.grad for v in params]
+            T.clip_grad_norm([gg for gg in gs if gg is not None], TRAIN["grad_clip"])
+            T.bert_adam_step([v.data for v in params], gs, state, lr=[TRAIN["lr"]] * len(params),
+                             weight_decay=[TRAIN["decay"]] * len(params), warmup=TRAIN["warmup"], t_total=TRAIN["t_total"])
         return float(loss)
 
-    return step, sample_B * S ** 3, "B=%d of the cfg-4 batch%s, full fwd+bwd (reference formulation, dropout %.1f)" % (
+    return step, sample_B * S ** 3, "B=%d of the cfg-4 batch%s, full fwd + BCE/Dice loss + bwd + BertAdam step (reference formulation, dropout %.1f)" % (
         sample_B, "" if crop == 1 else ", spatial crop 1/%d per axis" % crop, CFG["dropout"])
 
 
@@ -168,7 +180,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "Segtran3d BraTS 112^3x4ch translayers=1 attractors=1024 bs=4 hot path (flatten+"
-                                   "squeeze-expansion stack+head), fwd+bwd", "reference_sample": desc},
+                                   "squeeze-expansion stack+head), fwd + BCE/Dice loss + bwd + BertAdam step", "reference_sample": desc},
             "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -255,15 +267,26 @@ def run_b200(args):
     B, S, K = CFG["B"], CFG["S"], CFG["classes"]
     feat = torch.randn(B, CFG["C0"], *CFG["grid"], device=dev).requires_grad_()
     curr = torch.randn(B, CFG["Cf"], *CFG["sp1"], device=dev).requires_grad_()
-    G = torch.randn(B, K, S, S, S, device=dev) / (B * K * S ** 3)
+    from segtran_b200.train import FlatBertAdam, seg_loss
+    Y = (torch.rand(B, K, S, S, S, device=dev) > 0.7).float()              # synthetic n-hot masks
+    pw = torch.tensor(TRAIN["bce_weight"], device=dev)
+    pw = pw * (K - 1) / pw.sum()                                           # train3d.py:517-518
+    cw = torch.ones(K, device=dev)
+    cw[0] = 0
+    cw = cw / cw.sum()                                                     # train3d.py:686-690
     net.scales_printed = True
+    # the reference's optimiser on the hot-path parameters: BertAdam + --gradclip (train3d.py:334-355, :760-762); it
+    # re-points the parameters into one flat buffer, so it is built before the step is captured
+    opt = None if args.no_optimizer else FlatBertAdam(
+        [{"params": hot_params, "lr": TRAIN["lr"], "weight_decay": TRAIN["decay"]}], warmup=TRAIN["warmup"],
+        t_total=TRAIN["t_total"], grad_clip=TRAIN["grad_clip"], bucket=bucket)
 
     def compute():
         bucket.zero()
         feat.grad = None
         curr.grad = None
         logits = net.hot_path(feat, curr, None, (S, S, S))
-        loss = ops.dot(logits, G)
+        loss, _, _ = seg_loss(logits, Y, pw, cw, TRAIN["dice_w"])         # train3d.py:731-756
         loss.backward()
         return loss
 
@@ -277,6 +300,8 @@ def run_b200(args):
         loss = compute_fn()
         bucket.allreduce_async()
         bucket.wait()
+        if opt is not None:
+            opt.step()                          # after the gradient exchange; 3 launches + 1 memset, all on the device
         return loss
 
     def barrier():
@@ -328,6 +353,8 @@ def run_b200(args):
     hcurr = [torch.randn(B, CFG["Cf"], *CFG["sp1"]).pin_memory() for _ in range(2)]
     dfeat = [torch.empty_like(feat) for _ in range(2)]
     dcurr = [torch.empty_like(curr) for _ in range(2)]
+    hmask = [(torch.rand(B, K, S, S, S) > 0.7).to(torch.uint8).pin_memory() for _ in range(2)]   # n-hot labels, 1 B/voxel
+    dmask = [torch.empty(B, K, S, S, S, dtype=torch.uint8, device=dev) for _ in range(2)]
     hloss = torch.zeros(1).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
     ready = [torch.cuda.Event() for _ in range(2)]
@@ -339,6 +366,7 @@ def run_b200(args):
             copy_stream.wait_event(consumed[s])
             dfeat[s].copy_(hfeat[s], non_blocking=True)
             dcurr[s].copy_(hcurr[s], non_blocking=True)
+            dmask[s].copy_(hmask[s], non_blocking=True)
             ready[s].record(copy_stream)
 
     def e2e_step(i):
@@ -348,10 +376,12 @@ def run_b200(args):
         c = dcurr[s].detach().requires_grad_()
         bucket.zero()
         logits = net.hot_path(f, c, None, (S, S, S))
-        loss = ops.dot(logits, G)
+        loss, _, _ = seg_loss(logits, dmask[s].float(), pw, cw, TRAIN["dice_w"])
         loss.backward()
         bucket.allreduce_async()
         bucket.wait()
+        if opt is not None:
+            opt.step()
         consumed[s].record()
         hloss.copy_(loss.detach(), non_blocking=True)
 
@@ -375,7 +405,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te) / e2e_steps
-    h2d = (hfeat[0].numel() + hcurr[0].numel()) * 4
+    h2d = (hfeat[0].numel() + hcurr[0].numel()) * 4 + hmask[0].numel()
 
     if rank == 0:
         agg = timer.summarize()
@@ -421,11 +451,14 @@ def run_b200(args):
                            "global_batch": world * B, "tokens_per_sample": 2744, "parallelism": "dp%d" % world,
                            "l2": "inputs (2.4 GB/step) exceed the 126 MB L2; no explicit flush",
                            "grad_bucket_bytes": bucket.bytes(),
-                           "launch": "cuda-graph replay of fwd+loss+bwd" if use_graph else "eager"},
+                           "launch": "cuda-graph replay of fwd+loss+bwd" if use_graph else "eager",
+                           "loss": "BCEWithLogits(pos_weight) + per-class Dice on the 112^3 logits (train3d.py:731-756)",
+                           "optimizer": None if opt is None else "FlatBertAdam on the hot-path parameters incl. --gradclip "
+                                                                 "0.1 (optimization.py:90-164, train3d.py:760-762), in the step"},
                 "clocks": sampler.summary(),
                 "e2e": {"value": world * B * S ** 3 / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                        "note": "pinned host feature tensors, double-buffered H2D on a copy stream, loss read back"},
+                        "note": "pinned host feature tensors + uint8 n-hot labels, double-buffered H2D on a copy stream, loss read back"},
                 "gpu_launches": launches, "roofline": roof, "kernel_breakdown": breakdown,
                 "ms_per_step_instrumented": ms_instr, "host_enqueue_ms_per_step": host_ms, "kernel_ms_per_step": total_ms / args.steps,
                 "loss": float(hloss)}
@@ -445,6 +478,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-optimizer", action="store_true", help="leave the BertAdam update out of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -193,6 +193,31 @@ int sx_token_scores(const float* vf, const float* W, int32_t B, int32_t N, int32
 /* and its data gradient: dvf[b,n,f] = sum_k dt[b,k,n] W[k,f]   (F % 4 == 0) */
 int sx_token_scores_bwd(const float* dt, const float* W, int32_t B, int32_t N, int32_t F, int32_t K, float* dvf,
                         void* stream);
+/* -------------------------------------------------------------------------------------------
+ * Training-step tail: segmentation loss and BertAdam on flat buckets.
+ * Everything the step needs (loss scalars, clip coefficients, scheduled learning rates, the step
+ * counter) is produced and consumed on the device, so the step can be captured in a CUDA graph.
+ * ------------------------------------------------------------------------------------------- */
+/* loss = (1-dice_w) * BCEWithLogits(pos_weight)(logits, mask) + dice_w * sum_{k>=1} class_w[k] * dice_loss_indiv(sigmoid(logits[:,k]), mask[:,k])
+ * (train3d.py:731-756, utils/losses.py:47-60).  logits, mask: [B,K,V] fp32 (mask n-hot).  pos_weight, class_w: [K] or NULL (= ones).
+ * sums: [B*K*4] double workspace (zeroed here); out3 = {loss, ce, dice}; coef: [B*K*2] Dice gradient coefficients for the backward. */
+int sx_seg_loss_fwd(const float* logits, const float* mask, int32_t B, int32_t K, int64_t V, const float* pos_weight,
+                    const float* class_w, float dice_w, double* sums, float* out3, float* coef, void* stream);
+/* dlogits = (*gout or 1) * d loss / d logits; ce_scale = (1-dice_w) / (B*K*V); coef from sx_seg_loss_fwd */
+int sx_seg_loss_bwd(const float* logits, const float* mask, int32_t B, int32_t K, int64_t V, const float* pos_weight,
+                    const float* coef, float ce_scale, const float* gout, float* dlogits, void* stream);
+/* One optimiser step of the reference's BertAdam (optimization.py:90-164) preceded by the global gradient-norm clip of
+ * train3d.py:760-761, on flat fp32 buckets p, g, m, v.  The buckets are cut into segments (<= a few thousand elements of
+ * ONE parameter each): seg_param / seg_off / seg_len [nseg].  lr, wd: per-parameter [P].  schedule: SX_SCHED_*; t_total = -1
+ * disables the schedule.  step: device counter (read, then incremented).  sumsq [P] double, coef [P], lr_eff [P]: device
+ * workspaces.  total_norm: optional device float (the pre-clip global norm).  A parameter whose gradient is exactly zero is
+ * left untouched (the reference skips p.grad is None: never-used parameters). */
+enum { SX_SCHED_WARMUP_LINEAR = 0, SX_SCHED_WARMUP_CONSTANT = 1 };
+int sx_adam_step(float* p, const float* g, float* m, float* v, const int32_t* seg_param, const int64_t* seg_off,
+                 const int32_t* seg_len, int32_t nseg, int32_t P, const float* lr, const float* wd, double b1, double b2,
+                 double eps, float grad_clip, float max_grad_norm, float warmup, int64_t t_total, int32_t schedule,
+                 int64_t* step, double* sumsq, float* coef, float* lr_eff, float* total_norm, void* stream);
+
 /* 1-D linear resampling (align_corners=False) of x viewed as [outer, Lin, inner] -> [outer, Lout, inner];
  * F.interpolate(mode='bilinear'|'trilinear') == one pass per axis. */
 int sx_resize_axis_fwd(const float* x, int64_t outer, int32_t Lin, int32_t Lout, int64_t inner, float* y,

@@ -161,9 +161,69 @@ def gen_seg2d(name, seed=4):
     print(name, "out", tuple(y.shape), "max|out|", float(y.abs().max()))
 
 
+def gen_train():
+    """Loss (train3d.py:731-756) and optimiser (optimization.py BertAdam + train3d.py:760 global clip) fixtures, produced by
+    the reference's own functions."""
+    R.load()
+    from utils import losses as ref_losses            # /root/reference/code/utils/losses.py
+    import optimization as ref_opt                    # /root/reference/code/optimization.py
+    from oracle import train_oracle as T
+    torch.manual_seed(11)
+    B, K, sp = 2, 4, (6, 5, 8)
+    logits = (torch.randn(B, K, *sp) * 2.5).requires_grad_(True)
+    mask = (torch.rand(B, K, *sp) > 0.6).float()
+    pos_weight = T.normalised_bce_weight([0., 3, 1, 1.75], K)            # BraTS default (train3d.py:223, :517-518)
+    class_weights = T.default_class_weights(K)
+    dice_w = 0.5
+    bce = torch.nn.BCEWithLogitsLoss(pos_weight=pos_weight)
+    ce = bce(logits.permute([0, 2, 3, 4, 1]), mask.permute([0, 2, 3, 4, 1]))
+    soft = torch.sigmoid(logits)
+    dice = 0
+    for cls in range(1, K):
+        dice = dice + ref_losses.dice_loss_indiv(soft[:, cls], mask[:, cls]) * class_weights[cls]
+    loss = (1 - dice_w) * ce + dice_w * dice
+    (g,) = torch.autograd.grad(loss, [logits])
+    torch.save(dict(kind="train_loss", logits=logits.detach(), mask=mask, pos_weight=pos_weight,
+                    class_weights=class_weights, dice_w=dice_w, loss=loss.detach(), ce=ce.detach(), dice=dice.detach(),
+                    dlogits=g), os.path.join(OUT, "train_loss_tiny.pt"))
+    print("train_loss_tiny loss", float(loss), "ce", float(ce), "dice", float(dice))
+
+    # optimiser: 5 parameters in 3 groups, one of them never receives a gradient; 4 steps
+    torch.manual_seed(12)
+    shapes = [(33, 17), (64,), (5, 7, 3), (1,), (40, 9)]
+    params = [torch.nn.Parameter(torch.randn(*s) * 0.3) for s in shapes]
+    init = [p.detach().clone() for p in params]
+    lr, decay = 2e-3, 1e-2
+    groups = [{"params": [params[0], params[2], params[4]], "weight_decay": decay, "lr": lr},
+              {"params": [params[1]], "weight_decay": decay * 0.1, "lr": lr},
+              {"params": [params[3]], "weight_decay": 0.0, "lr": lr * 100}]
+    per_lr = [lr, lr, lr, lr * 100, lr]
+    per_wd = [decay, decay * 0.1, decay, 0.0, decay]
+    t_total, warm = 8, 0.25
+    opt = ref_opt.BertAdam(groups, warmup=warm, t_total=t_total, weight_decay=decay)
+    grads, after = [], []
+    for step in range(4):
+        gs = [torch.randn(*s) * (10.0 if step == 1 else 0.02) for s in shapes]      # step 1 trips both clips
+        gs[4] = None                                                                    # never-used parameter
+        grads.append([None if g is None else g.clone() for g in gs])
+        opt.zero_grad()
+        for p, g in zip(params, gs):
+            p.grad = None if g is None else g.clone()
+        torch.nn.utils.clip_grad_norm_(params, 0.1)                                     # train3d.py:760-761
+        opt.step()
+        after.append([p.detach().clone() for p in params])
+    torch.save(dict(kind="train_bertadam", shapes=shapes, init=init, grads=grads, after=after, lr=per_lr,
+                    weight_decay=per_wd, t_total=t_total, warmup=warm, grad_clip=0.1, max_grad_norm=0.05),
+               os.path.join(OUT, "train_bertadam_tiny.pt"))
+    print("train_bertadam_tiny: 4 steps, |p0| after", float(after[-1][0].abs().max()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        gen_train()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         gen_encoder("enc2d_nosqueeze", [64, 64], 4, 8, 2, True, (6, 7), 2, seed=21, squeeze=False)
         gen_encoder("enc3d_sqffn", [64, 64], 4, 16, 3, True, (3, 4, 5), 2, seed=22, sq_ffn=True)

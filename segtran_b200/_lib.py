@@ -16,6 +16,7 @@ SX_OP_TF32, SX_OP_BF16 = 0, 1
 SX_MAJOR_K, SX_MAJOR_MN = 0, 1
 SX_BIAS_NONE, SX_BIAS_N, SX_BIAS_M = 0, 1, 2
 SX_ACT_NONE, SX_ACT_GELU, SX_ACT_GELU_BWD = 0, 1, 2
+SX_SCHED_WARMUP_LINEAR, SX_SCHED_WARMUP_CONSTANT = 0, 1
 
 
 class SxError(RuntimeError):
@@ -37,7 +38,7 @@ class sx_gemm_args(C.Structure):
                 ("_pad3", C.c_uint32), ("drop_seed", C.c_uint64), ("drop_seed_dev", C.c_void_p), ("addend", C.c_void_p)]
 
 
-_P, _I, _L, _F, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
+_P, _I, _L, _F, _U64, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_double
 
 # name -> argtypes (every function returns int; 0 = success)
 _PROTOS = {
@@ -72,6 +73,9 @@ _PROTOS = {
     "sx_token_scores_bwd": [_P, _P, _I, _I, _I, _I, _P, _P],
     "sx_resize_axis_fwd": [_P, _L, _I, _I, _L, _P, _I, _P],
     "sx_resize_axis_bwd": [_P, _L, _I, _I, _L, _P, _P],
+    "sx_seg_loss_fwd": [_P, _P, _I, _I, _L, _P, _P, _F, _P, _P, _P, _P],
+    "sx_seg_loss_bwd": [_P, _P, _I, _I, _L, _P, _P, _F, _P, _P, _P],
+    "sx_adam_step": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _D, _D, _D, _F, _F, _F, _L, _I, _P, _P, _P, _P, _P, _P],
     "sx_sgemm_small": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _L, _L, _L, _F, _I, _P],
 }
 # every symbol include/segtran_b200.h declares (checked by tests/test_abi.py)

@@ -17,6 +17,9 @@ import torch
 import torch.distributed as dist
 
 
+_ALIGN = 64          # elements (256 bytes of fp32)
+
+
 class GradBucket:
     def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None, overlap_chunks: int = 0,
                  direct_accumulate: bool = False):
@@ -28,13 +31,16 @@ class GradBucket:
         if not self.params:
             raise ValueError("GradBucket: no trainable parameters")
         dev, dt = self.params[0].device, self.params[0].dtype
-        self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
-        off = 0
+        # every parameter starts on a 256-byte boundary of the bucket (TMA / vector accesses on the views stay legal when
+        # an optimiser lays the parameters out the same way); the padding stays zero and rides along in the all-reduce
+        self.offsets, off = [], 0
         for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)      # autograd accumulates in place into the bucket
-            off += n
+            self.offsets.append(off)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = off
+        self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.flat[off:off + p.numel()].view_as(p)      # autograd accumulates in place into the bucket
         # direct_accumulate: the weight-gradient GEMMs of the hot path add straight into these views (ops.set_grad_sink)
         # instead of producing a temporary that autograd adds in a second pass; needs zero() before every step, and the
         # per-parameter hooks of the overlap mode do not fire for those parameters
@@ -59,7 +65,7 @@ class GradBucket:
             off, start, members = 0, 0, []
             for p in self.params:
                 members.append(p)
-                off += p.numel()
+                off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
                 if off - start >= target:
                     self._chunks.append({"lo": start, "hi": off, "n": len(members), "left": len(members), "sent": False})
                     for q in members:
@@ -96,12 +102,10 @@ class GradBucket:
 
     def reattach(self):
         """Call if something replaced p.grad (e.g. zero_grad(set_to_none=True))."""
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             n = p.numel()
             if p.grad is None or p.grad.data_ptr() != self.flat[off:off + n].data_ptr():
                 p.grad = self.flat[off:off + n].view_as(p)
-            off += n
 
     def allreduce_async(self):
         """Average the bucket over ranks; returns immediately (the transfer runs on a side stream on GPUs)."""
@@ -155,4 +159,5 @@ class GradBucket:
             self.flat.mul_(1.0 / self.world)
 
     def bytes(self) -> int:
+        """bytes moved by the all-reduce (parameters + alignment padding)"""
         return self.numel * self.flat.element_size()
