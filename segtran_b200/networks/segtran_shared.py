@@ -227,7 +227,10 @@ class ExpandedFeatTrans(nn.Module):
     def forward(self, input_feat, attention_probs, in_geoshape=None):
         """input_feat [B,U2,C]; attention_probs [B,M,U1,U2] -> [B,U1,F]."""
         M = self.num_modes
-        v = ops.linear(input_feat, self.first_linear.weight, self.first_linear.bias)         # [B,U2,M*F]
+        fold = self.has_FFN and isinstance(self.output, MMPrivateOutput) and isinstance(self.intermediate, MMSharedMid) \
+            and self.first_linear.bias is None and self.first_linear.weight.shape[1] % 4 == 0 and self.feat_dim % 4 == 0
+        if not fold:
+            v = ops.linear(input_feat, self.first_linear.weight, self.first_linear.bias)     # [B,U2,M*F]
         if not self.has_FFN:
             if M != 1:
                 _unsupported("the no-FFN branch with more than one mode (Polyformer)")
@@ -237,9 +240,14 @@ class ExpandedFeatTrans(nn.Module):
             # (P V) Wm^T = P (V Wm^T): push the value bank (U2 rows) through the shared mid Linear instead of the
             # fused tokens (U1 rows), and fuse MMSharedMid's bias + GELU + dropout into the P.V epilogue.  U itself
             # is only needed by the (discarded) residual of MMPrivateOutput, so it is never materialised.
+            # With a bias-free value projection the two Linears on the bank fold into one weight-space product
+            # W'_m = Wm Wv_m (batch-independent), so the bank is projected once.
             mid = self.intermediate
             B, U2 = input_feat.shape[0], input_feat.shape[1]
-            vp = ops.linear(v.view(B, U2, M, self.feat_dim), mid.shared_linear.weight).view(B, U2, M * self.feat_dim)
+            if fold:
+                vp = ops.folded_value_bank(input_feat, self.first_linear.weight, mid.shared_linear.weight, M)
+            else:
+                vp = ops.linear(v.view(B, U2, M, self.feat_dim), mid.shared_linear.weight).view(B, U2, M * self.feat_dim)
             p = mid.dropout.p if self.training else 0.0
             # ... and MMPrivateOutput's grouped Linear rides in the same autograd node (its backward fuses GELU' and
             # the dropout mask into the dG GEMM epilogue)

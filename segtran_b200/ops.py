@@ -620,6 +620,60 @@ class _AttnPVGelu(torch.autograd.Function):
         return dP, dv, None, db, None, None
 
 
+class _FoldedValueBank(torch.autograd.Function):
+    """V'[b,a,m*F+o] = sum_f Wm[o,f] (a[b] Wv[m*F+f,:]^T) = a[b] . W'[m*F+o,:],  W'_m = Wm Wv_m   (segtran_shared.py:414 then
+    :243 applied to the attractor rows, see ExpandedFeatTrans.forward): the value projection and MMSharedMid's Linear
+    folded into ONE weight-space product (M F^2 C MACs, batch-independent) and ONE projection of the A attractor rows."""
+
+    @staticmethod
+    def forward(ctx, a, Wv, Wm, M):
+        B, A, Cd = a.shape
+        Fd = Wm.shape[0]
+        a2 = a.reshape(B * A, Cd)
+        if not a2.is_contiguous():
+            a2 = a2.contiguous()
+        Wvr = round_tf32(Wv).view(M, 1, Fd, Cd)                       # [m, f, c]
+        Wmr = round_tf32(Wm)                                          # [o, f]
+        Wf = gemm_nt(Wmr.view(1, 1, Fd, Fd), Wvr.transpose(-1, -2))   # [M,1,F(o),C] = Wm Wv_m, TF32-rounded
+        Vp = gemm_nt(a2, Wf.view(M * Fd, Cd))[0, 0]                   # [B*A, M*F]
+        ctx.save_for_backward(a2, Wf, Wvr, Wmr)
+        ctx.meta = (B, A, Cd, Fd, M, Wv.shape)
+        ctx.leaves = (Wv, Wm)
+        return Vp.view(B, A, M * Fd)
+
+    @staticmethod
+    def backward(ctx, dVp):
+        a2, Wf, Wvr, Wmr = ctx.saved_tensors
+        B, A, Cd, Fd, M, wv_shape = ctx.meta
+        Wv, Wm = ctx.leaves
+        d2 = dVp.reshape(B * A, M * Fd)
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        da = dWv = dWm = None
+        if ctx.needs_input_grad[0]:
+            da = gemm_nt(d2, Wf.view(M * Fd, Cd).t(), round_out=False)[0, 0].view(B, A, Cd)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dWf = gemm_nt(d2.t(), a2.t(), round_out=False).view(M, 1, Fd, Cd)          # [m, o, c]
+            if ctx.needs_input_grad[2]:                               # dWm[o,f] = sum_m dW'_m[o,:] . Wv_m[f,:]
+                tgt = _grad_target(Wm)
+                if tgt is not None:
+                    gemm_nt(dWf, Wvr, out=tgt.view(1, 1, Fd, Fd), reduce_z1=True, accumulate=True, round_out=False)
+                else:
+                    dWm = gemm_nt(dWf, Wvr, reduce_z1=True, round_out=False).view(Fd, Fd)
+            if ctx.needs_input_grad[1]:                               # dWv_m[f,c] = sum_o Wm[o,f] dW'_m[o,c]
+                tgt = _grad_target(Wv)
+                if tgt is not None:
+                    gemm_nt(Wmr.t().view(1, 1, Fd, Fd), dWf.transpose(-1, -2), out=tgt.view(M, 1, Fd, Cd), accumulate=True,
+                            round_out=False)
+                else:
+                    dWv = gemm_nt(Wmr.t().view(1, 1, Fd, Fd), dWf.transpose(-1, -2), round_out=False).view(wv_shape)
+        return da, dWv, dWm, None
+
+
+def folded_value_bank(a, Wv, Wm, M):
+    return _FoldedValueBank.apply(a, Wv, Wm, M)
+
+
 def attn_pv_gelu(P, v, M, bias, drop_p=0.0, seed=0):
     return _AttnPVGelu.apply(P, v, M, bias, drop_p, seed)
 
