@@ -195,6 +195,7 @@ class KernelTimer:
     def __init__(self):
         self.records = []                       # (name, info, ev0, ev1)
         self.shapes = []
+        self.gemm_bytes = []
         self.enabled = False
 
     @contextlib.contextmanager
@@ -207,6 +208,10 @@ class KernelTimer:
         if name == "sx_gemm":
             g = cargs[0]._obj
             info = 2.0 * g.M * g.N * g.K * g.Z0 * g.Z1
+            za = (g.Z0 if g.A.stride_z0 else 1) * (g.Z1 if g.A.stride_z1 else 1)      # broadcast operands are read once
+            zb = (g.Z0 if g.B.stride_z0 else 1) * (g.Z1 if g.B.stride_z1 else 1)
+            zc = (g.Z0 if g.c_stride_z0 or g.Z0 == 1 else 1) * (g.Z1 if g.c_stride_z1 or g.Z1 == 1 else 1)
+            self.gemm_bytes.append(4.0 * (g.M * g.K * za + g.N * g.K * zb + g.M * g.N * zc * (2 if g.preact else 1)))
             self.shapes.append("%dx%dx%d z%d %s%s sk%d" % (g.M, g.N, g.K, g.Z0 * g.Z1, "kM"[g.A.major], "kM"[g.B.major],
                                                           g.split_k))
         elif name.startswith("sx_head_contract"):
@@ -228,6 +233,25 @@ class KernelTimer:
                 i += 1
         return {k: {"ms": v[0] / v[2], "tflops": v[1] / v[0] / 1e9, "n": v[2]} for k, v in
                 sorted(out.items(), key=lambda kv: -kv[1][0])}
+
+    def gemm_roofline(self, peak_tflops, peak_gbs):
+        """Per-launch roofline: bound_i = max(flops_i / tensor peak, algorithmic bytes_i / HBM peak).  Returns the sum of
+        the bounds over the sum of the measured times, and the time split between tensor-bound and HBM-bound launches."""
+        i, tb, tt, hb, ht = 0, 0.0, 0.0, 0.0, 0.0
+        for name, info, e0, e1 in self.records:
+            if name != "sx_gemm":
+                continue
+            ms = e0.elapsed_time(e1)
+            t_f = info / (peak_tflops * 1e12) * 1e3
+            t_b = self.gemm_bytes[i] / (peak_gbs * 1e9) * 1e3
+            if t_f >= t_b:
+                tb, tt = tb + t_f, tt + ms
+            else:
+                hb, ht = hb + t_b, ht + ms
+            i += 1
+        return {"frac_of_bound": (tb + hb) / max(tt + ht, 1e-9),
+                "tensor_bound_launches": {"ms": tt, "frac": tb / max(tt, 1e-9)},
+                "hbm_bound_launches": {"ms": ht, "frac": hb / max(ht, 1e-9)}}
 
     def summarize(self):
         agg = {}
@@ -431,6 +455,14 @@ def run_b200(args):
                     "executed_tflop_per_step": kwork / args.steps / 1e12,
                     "peak_source": "%s bf16 sustained / 2 (tf32 rate)" % src, "launches": kcount,
                     "share_of_step": kms / total_ms}
+            # mixed shapes: some launches of the same kernel are HBM-bound by the roofline model itself (the head's
+            # weight gradient streams 2.3 GB for 5 GFLOP) — per-launch bound = max(flops/peak, algorithmic bytes/HBM peak)
+            hbm_peak = peaks.get("hbm_gbs", 6570.0)
+            pl = timer.gemm_roofline(peak, hbm_peak)
+            for v in pl.values():
+                if isinstance(v, dict):
+                    v["ms"] /= args.steps
+            roof["per_launch"] = pl
         else:
             src = "measured" if "hbm_gbs" in peaks else "fallback"
             peak = peaks.get("hbm_gbs", 6650.0)
