@@ -25,14 +25,11 @@ constexpr int BM = 128;          // tile rows   (UMMA M)
 constexpr int BN = 256;          // tile cols   (UMMA N)
 constexpr int BKB = 128;         // bytes of K per stage row (one 128B swizzle span)
 constexpr int KSTEPS = 4;        // UMMA instructions per stage (each covers 32 bytes of K)
-constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BKB;       // 16 KB
-constexpr int B_STAGE_BYTES = BN * BKB;       // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 384;         // warps 0-3: TMA / MMA / TMEM alloc / idle;  warps 4-11: epilogue (2 per lane quarter)
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = 192 * 1024 /*4 x 48 KB or 6 x 32 KB stages*/ + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct GemmParams {
   int M, N, K, Z0, Z1;
@@ -75,10 +72,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-template <int ES, bool A_MN, bool B_MN>
+// CG2: CTA-pair mode (tcgen05 cta_group::2).  The two CTAs of a 2-cluster compute one 256 x 256 tile: each loads its own
+// 128 rows of A and HALF of the B tile (128 of the 256 columns), the leader (even) CTA issues 256-row UMMAs that read A
+// and B from both CTAs' shared memory, and each CTA drains its own 128 accumulator rows from its own TMEM.  Per CTA and
+// k-block that is 32 KB of operand traffic instead of 48 KB (the main loop of the 1-CTA kernel lives on L2 bandwidth at
+// K <= 1024) and a 6-deep instead of a 4-deep ring in the same shared memory.
+template <int ES, bool A_MN, bool B_MN, bool CG2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr bool kTF32 = (ES == 4);
+  constexpr int BNL = CG2 ? BN / 2 : BN;         // B-tile columns loaded by this CTA
+  constexpr int B_STAGE_BYTES = BNL * BKB;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int STAGES = CG2 ? 6 : 4;            // 6 x 32 KB = 4 x 48 KB
+  const uint32_t rank = CG2 ? sx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int cid = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // tile-loop start / stride in units of
+  const int ncl = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;           // CTAs (1-CTA mode) or CTA pairs
   constexpr int BK = BKB / ES;                 // elements of K per stage: 64 (bf16) / 32 (tf32)
   constexpr int UMMA_K = 32 / ES;              // 16 / 8
   constexpr int MN_BOX = BKB / ES;             // contiguous MN elements per MN-major box: 64 / 32
@@ -110,16 +120,22 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       sx::mbar_init(&tfull_bar[a], 1);
-      sx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
+      sx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS * (CG2 ? 2 : 1));    // pair mode: both CTAs' epilogues -> leader
     }
     sx::fence_barrier_init();
   }
   if (warp == 2) {
-    sx::tmem_alloc(tmem_slot, TMEM_COLS);
-    sx::tmem_relinquish();
+    if constexpr (CG2) {
+      sx::tmem_alloc2(tmem_slot, TMEM_COLS);
+      sx::tmem_relinquish2();
+    } else {
+      sx::tmem_alloc(tmem_slot, TMEM_COLS);
+      sx::tmem_relinquish();
+    }
   }
   sx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) sx::cluster_sync();        // the peer's barriers must exist before anything signals them
+  else __syncthreads();
   sx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -141,48 +157,54 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // operand tiles are re-read by every CTA of the same tile row / column: keep them in L2 while a large
       // output streams through
       const uint64_t pol = p.stream_out ? sx::kEvictLast : sx::kEvictNormal;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      auto load = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+        if constexpr (CG2) sx::tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3, pol);   // bytes credited to the leader
+        else sx::tma_load_4d(dst, m, bar, c0, c1, c2, c3, pol);
+      };
+      for (int t = cid; t < p.total_tiles; t += ncl) {
         int z0, z1, mb, nb, ks;
         decode(t, z0, z1, mb, nb, ks);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         const int az0 = p.a_uses_z0 ? z0 : 0, az1 = p.a_uses_z1 ? z1 : 0;
         const int bz0 = p.b_uses_z0 ? z0 : 0, bz1 = p.b_uses_z1 ? z1 : 0;
+        const int m0 = mb * (CG2 ? 2 * BM : BM) + (int)rank * BM;       // this CTA's A rows
+        const int n0 = nb * BN + (int)rank * BNL;                       // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           sx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          sx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (leader) sx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES * (CG2 ? 2 : 1));
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           const int k0 = kb * BK;
           if constexpr (!A_MN) {
-            sx::tma_load_4d(sa, &tmA, &full_bar[stage], k0, mb * BM, az0, az1, pol);
+            load(sa, &tmA, &full_bar[stage], k0, m0, az0, az1);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / MN_BOX; ++j)
-              sx::tma_load_4d(sa + j * MN_BOX_BYTES, &tmA, &full_bar[stage], mb * BM + j * MN_BOX, k0, az0, az1, pol);
+              load(sa + j * MN_BOX_BYTES, &tmA, &full_bar[stage], m0 + j * MN_BOX, k0, az0, az1);
           }
           if constexpr (!B_MN) {
-            sx::tma_load_4d(sb, &tmB, &full_bar[stage], k0, nb * BN, bz0, bz1, pol);
+            load(sb, &tmB, &full_bar[stage], k0, n0, bz0, bz1);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / MN_BOX; ++j)
-              sx::tma_load_4d(sb + j * MN_BOX_BYTES, &tmB, &full_bar[stage], nb * BN + j * MN_BOX, k0, bz0, bz1, pol);
+            for (int j = 0; j < BNL / MN_BOX; ++j)
+              load(sb + j * MN_BOX_BYTES, &tmB, &full_bar[stage], n0 + j * MN_BOX, k0, bz0, bz1);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (pair mode: the leader CTA only) =====================
     // cute::UMMA::InstrDescriptor: c_format[4,6)=1 (F32), a_format[7,10), b_format[10,13) (1=BF16, 2=TF32),
     // a_major bit 15, b_major bit 16 (1 = MN-major), n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
     constexpr uint32_t fmt = kTF32 ? 2u : 1u;
     constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) |
-                               ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                               ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((CG2 ? 2 * BM : BM) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    for (int t = cid; t < p.total_tiles; t += ncl, ++it) {
       int z0, z1, mb, nb, ks;
       decode(t, z0, z1, mb, nb, ks);
       const int kb0 = ks * p.kb_per_split;
@@ -207,10 +229,16 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < KSTEPS; ++k) {
             const uint64_t dak = da + (uint64_t)(k * (A_MN ? ADV_MN : ADV_K));
             const uint64_t dbk = db + (uint64_t)(k * (B_MN ? ADV_MN : ADV_K));
-            sx::umma<kTF32>(tmem_d, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CG2) sx::umma_pair<kTF32>(tmem_d, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else sx::umma<kTF32>(tmem_d, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          sx::umma_commit(&empty_bar[stage]);                 // frees the smem stage when these MMAs retire
-          if (kb == kb1 - 1) sx::umma_commit(&tfull_bar[acc]);  // accumulator complete
+          if constexpr (CG2) {
+            sx::umma_commit_pair(&empty_bar[stage]);                 // frees the stage in BOTH CTAs
+            if (kb == kb1 - 1) sx::umma_commit_pair(&tfull_bar[acc]);  // wakes both CTAs' epilogues
+          } else {
+            sx::umma_commit(&empty_bar[stage]);                 // frees the smem stage when these MMAs retire
+            if (kb == kb1 - 1) sx::umma_commit(&tfull_bar[acc]);  // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -292,14 +320,14 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     };
 
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    for (int t = cid; t < p.total_tiles; t += ncl, ++it) {
       int z0, z1, mb, nb, ks;
       decode(t, z0, z1, mb, nb, ks);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       sx::mbar_wait(&tfull_bar[acc], acc_phase);
       sx::tc_fence_after();
-      const int row0 = mb * BM + q * 32;
+      const int row0 = mb * (CG2 ? 2 * BM : BM) + (int)rank * BM + q * 32;
       const long long zoff = (long long)z1 * p.c_sz1 + (long long)z0 * p.c_sz0;
       const float* bias = p.bias ? p.bias + (long long)z1 * p.bias_sz1 + (long long)z0 * p.bias_sz0 : nullptr;
       const bool add_bias = (bias != nullptr) && (ks == 0);
@@ -420,7 +448,10 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       sx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) sx::mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CG2) sx::mbar_arrive_leader(&tempty_bar[acc]);
+        else sx::mbar_arrive(&tempty_bar[acc]);
+      }
     }
     if (p.amax) {
       tmax = sx::warp_max(tmax);
@@ -429,10 +460,12 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   sx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) sx::cluster_sync();        // the peer may still read this CTA's operands / signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     sx::tc_fence_after();
-    sx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CG2) sx::tmem_dealloc2(tmem_base, TMEM_COLS);
+    else sx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -462,6 +495,7 @@ struct DebugKnobs {
   long long max_ctas = -1;
   long long dbg_epi = 0;
   long long stream_out = -1;      // -1: automatic
+  long long cg2 = -1;             // CTA-pair kernel: -1 automatic, 0 never, 1 whenever the shape allows it
 };
 DebugKnobs g_knobs;
 
@@ -507,16 +541,32 @@ int make_map(CUtensorMap* tm, const sx_operand& op, int es, int rows, int K, int
   return 0;
 }
 
-template <int ES, bool A_MN, bool B_MN>
+template <int ES, bool A_MN, bool B_MN, bool CG2>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
-  auto kern = sx_gemm_kernel<ES, A_MN, B_MN>;
+  auto kern = sx_gemm_kernel<ES, A_MN, B_MN, CG2>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   SX_CHECK_CUDA(attr_err);
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  if constexpr (CG2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  } else {
+    kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  }
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -544,6 +594,7 @@ extern "C" int sx_gemm_debug_set(const char* key, int64_t value) {
   else if (k == "max_ctas") g_knobs.max_ctas = value;
   else if (k == "dbg_epi") g_knobs.dbg_epi = value;
   else if (k == "stream_out") g_knobs.stream_out = value;
+  else if (k == "cg2") g_knobs.cg2 = value;
   else {
     sx_set_error("sx_gemm_debug_set: unknown key %s", key);
     return -1;
@@ -562,9 +613,25 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
   const int sms = sm_count_cached();
   SX_REQUIRE(sms > 0, "sx_gemm: no CUDA device (this library has no CPU fallback)");
 
+  // CTA-pair kernel (TF32 only): automatic for shapes with at least one full wave of 256-row tiles
+  bool cg2 = false;
+  if (es == 4 && g_knobs.cg2 != 0 && sms >= 2) {
+    if (g_knobs.cg2 > 0) {
+      cg2 = true;
+    } else if (a->M > BM) {
+      // a pair tile on a CTA pair takes ~0.8x the time of a 128-row tile on one SM (measured: 913 vs 726 TFLOP/s at
+      // K=1024, 1020 vs 808 at K=4096); use the pair kernel unless its wave quantisation eats that
+      int nkb = sx_ceil_div(a->K, bk), split = a->split_k < 1 ? 1 : (a->split_k > nkb ? nkb : a->split_k);
+      split = sx_ceil_div(nkb, sx_ceil_div(nkb, split));
+      const long long zs = (long long)sx_ceil_div(a->N, BN) * a->Z0 * a->Z1 * split;
+      const long long w1 = sx_ceil_div((long long)sx_ceil_div(a->M, BM) * zs, sms);
+      const long long w2 = sx_ceil_div((long long)sx_ceil_div(a->M, 2 * BM) * zs, sms / 2);
+      cg2 = (double)w2 * 0.85 <= (double)w1;
+    }
+  }
   GemmParams p{};
   p.M = a->M; p.N = a->N; p.K = a->K; p.Z0 = a->Z0; p.Z1 = a->Z1;
-  p.tiles_m = sx_ceil_div(a->M, BM);
+  p.tiles_m = sx_ceil_div(a->M, cg2 ? 2 * BM : BM);
   p.tiles_n = sx_ceil_div(a->N, BN);
   p.num_kb = sx_ceil_div(a->K, bk);
   int split = a->split_k < 1 ? 1 : a->split_k;
@@ -608,22 +675,28 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
   CUtensorMap ta, tb;
   int rc = make_map(&ta, a->A, es, a->M, a->K, a->Z0, a->Z1, BM, "A");
   if (rc) return rc;
-  rc = make_map(&tb, a->B, es, a->N, a->K, a->Z0, a->Z1, BN, "B");
+  rc = make_map(&tb, a->B, es, a->N, a->K, a->Z0, a->Z1, cg2 ? BN / 2 : BN, "B");
   if (rc) return rc;
 
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  if (g_knobs.max_ctas > 0 && grid > g_knobs.max_ctas) grid = (int)g_knobs.max_ctas;
+  if (cg2) grid = 2 * (p.total_tiles < sms / 2 ? p.total_tiles : sms / 2);       // CTA pairs
+  if (g_knobs.max_ctas > 0 && grid > g_knobs.max_ctas) grid = (int)g_knobs.max_ctas & (cg2 ? ~1 : ~0);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool amn = a->A.major == SX_MAJOR_MN, bmn = a->B.major == SX_MAJOR_MN;
-  if (es == 4) {
-    if (!amn && !bmn) return launch<4, false, false>(ta, tb, p, grid, st);
-    if (!amn && bmn) return launch<4, false, true>(ta, tb, p, grid, st);
-    if (amn && !bmn) return launch<4, true, false>(ta, tb, p, grid, st);
-    return launch<4, true, true>(ta, tb, p, grid, st);
+  if (es == 4 && cg2) {
+    if (!amn && !bmn) return launch<4, false, false, true>(ta, tb, p, grid, st);
+    if (!amn && bmn) return launch<4, false, true, true>(ta, tb, p, grid, st);
+    if (amn && !bmn) return launch<4, true, false, true>(ta, tb, p, grid, st);
+    return launch<4, true, true, true>(ta, tb, p, grid, st);
+  } else if (es == 4) {
+    if (!amn && !bmn) return launch<4, false, false, false>(ta, tb, p, grid, st);
+    if (!amn && bmn) return launch<4, false, true, false>(ta, tb, p, grid, st);
+    if (amn && !bmn) return launch<4, true, false, false>(ta, tb, p, grid, st);
+    return launch<4, true, true, false>(ta, tb, p, grid, st);
   } else {
-    if (!amn && !bmn) return launch<2, false, false>(ta, tb, p, grid, st);
-    if (!amn && bmn) return launch<2, false, true>(ta, tb, p, grid, st);
-    if (amn && !bmn) return launch<2, true, false>(ta, tb, p, grid, st);
-    return launch<2, true, true>(ta, tb, p, grid, st);
+    if (!amn && !bmn) return launch<2, false, false, false>(ta, tb, p, grid, st);
+    if (!amn && bmn) return launch<2, false, true, false>(ta, tb, p, grid, st);
+    if (amn && !bmn) return launch<2, true, false, false>(ta, tb, p, grid, st);
+    return launch<2, true, true, false>(ta, tb, p, grid, st);
   }
 }
