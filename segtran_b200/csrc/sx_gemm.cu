@@ -29,7 +29,9 @@ constexpr int A_STAGE_BYTES = BM * BKB;       // 16 KB
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 384;         // warps 0-3: TMA / MMA / TMEM alloc / idle;  warps 4-11: epilogue (2 per lane quarter)
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int SMEM_BYTES = 192 * 1024 /*4 x 48 KB or 6 x 32 KB stages*/ + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = 192 * 1024 /*4 x 48 KB stages*/ + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STG_WARP_BYTES = 2 * 2048;     // pair kernel: per-epilogue-warp double buffer of 16 x 32 fp32 for TMA stores
+constexpr int SMEM_BYTES_CG2 = 6 * 32 * 1024 + NUM_EPI_WARPS * STG_WARP_BYTES + 1024 + 256;   // 6 stages + 32 KB staging
 
 struct GemmParams {
   int M, N, K, Z0, Z1;
@@ -56,6 +58,7 @@ struct GemmParams {
   unsigned int lbo_k, sbo_k, lbo_mn_a, lbo_mn_b, sbo_mn, desc_version;
   int dbg_epi;      // bring-up: 0 normal, 1 skip global stores, 2 skip TMEM loads too
   int stream_out;   // output larger than half the L2: store with evict-first (st.global.cs), keep operands (evict-last)
+  int c_tma;        // pair kernel: C (and preact) leave through shared memory + TMA bulk stores (full 128-byte lines)
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
@@ -79,12 +82,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // K <= 1024) and a 6-deep instead of a 4-deep ring in the same shared memory.
 template <int ES, bool A_MN, bool B_MN, bool CG2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const GemmParams p) {
   constexpr bool kTF32 = (ES == 4);
   constexpr int BNL = CG2 ? BN / 2 : BN;         // B-tile columns loaded by this CTA
   constexpr int B_STAGE_BYTES = BNL * BKB;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  constexpr int STAGES = CG2 ? 6 : 4;            // 6 x 32 KB = 4 x 48 KB
+  constexpr int STAGES = CG2 ? 6 : 4;            // 6 x 32 KB (+ 32 KB of store staging) or 4 x 48 KB
   const uint32_t rank = CG2 ? sx::cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const int cid = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // tile-loop start / stride in units of
@@ -99,7 +103,8 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* stg = smem + STAGES * STAGE_BYTES;            // pair kernel: TMA-store staging, 1 KB aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + (CG2 ? NUM_EPI_WARPS * STG_WARP_BYTES : 0));
   uint64_t* full_bar = bars;                   // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;         // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]       MMA -> epilogue
@@ -297,6 +302,38 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     };
 
+    // pair kernel: fragment -> this warp's swizzled 16 x 32 staging tiles -> TMA bulk stores (complete 128-byte lines,
+    // asynchronous, clipped at the tensor edge by the hardware); the two 16-row halves of a fragment alternate between
+    // two 2 KB buffers, so filling one overlaps the TMA engine reading the other
+    int sbuf = 0;
+    auto tma_store = [&](const CUtensorMap* tm, const float (&f)[32], int row0, int col0, int z0, int z1) {
+#pragma unroll
+      for (int P = 0; P < 2; ++P) {
+        uint8_t* buf = stg + (warp - 4) * STG_WARP_BYTES + (sbuf & 1) * 2048;
+        if (lane == 0) sx::tma_store_wait_read<1>();       // the store issued two halves ago has released this buffer
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = 8 * h + tr;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = 8 * j + tc;
+            const int i0 = 16 * P + 4 * j + 2 * h;
+            // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
+            float2* dst = reinterpret_cast<float2*>(buf + r * 128 + ((((col >> 2) ^ (r & 7)) << 4) | ((col & 3) << 2)));
+            *dst = make_float2(f[i0], f[i0 + 1]);
+          }
+        }
+        sx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          sx::tma_store_4d(tm, buf, col0, row0 + 16 * P, z0, z1);
+          sx::tma_store_commit();
+        }
+        ++sbuf;
+      }
+    };
+
     // fp32 tensor in C's layout -> the same fragment distribution (out-of-range elements read as 0)
     auto load_frag = [&](const float* base, float (&g)[32], long long zoff, int row0, int col0) {
 #pragma unroll
@@ -382,7 +419,10 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] *= sx::gelu_erf_grad(g[i]);
         } else {
-          if (p.preact) store_frag(p.preact, f, zoff, row0, col0, false);
+          if (p.preact) {
+            if (CG2 && p.c_tma) tma_store(&tmP, f, row0, col0, z0, z1);
+            else store_frag(p.preact, f, zoff, row0, col0, false);
+          }
           if (p.act == SX_ACT_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = sx::gelu_erf(f[i]);
@@ -444,7 +484,8 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (col0 + 8 * j + tc + e < p.N) tmax = fmaxf(tmax, f[16 * P + 4 * j + 2 * h + e]);
               }
         }
-        store_frag(p.C, f, zoff, row0, col0, p.accumulate != 0);
+        if (CG2 && p.c_tma) tma_store(&tmC, f, row0, col0, z0, z1);
+        else store_frag(p.C, f, zoff, row0, col0, p.accumulate != 0);
       }
       sx::tc_fence_before();
       __syncwarp();
@@ -457,6 +498,7 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tmax = sx::warp_max(tmax);
       if (lane == 0 && tmax > -3.0e38f) sx::atomic_max_float(p.amax, tmax);
     }
+    if (CG2 && p.c_tma && lane == 0) sx::tma_store_wait_all();
   }
 
   sx::tc_fence_before();
@@ -496,6 +538,7 @@ struct DebugKnobs {
   long long dbg_epi = 0;
   long long stream_out = -1;      // -1: automatic
   long long cg2 = -1;             // CTA-pair kernel: -1 automatic, 0 never, 1 whenever the shape allows it
+  long long c_tma = -1;           // pair kernel TMA-store epilogue: 0 off, otherwise automatic
 };
 DebugKnobs g_knobs;
 
@@ -541,20 +584,40 @@ int make_map(CUtensorMap* tm, const sx_operand& op, int es, int rows, int K, int
   return 0;
 }
 
+// fp32 output tensor [Z1][Z0][M][N] (row pitch ldc) as a 4-D tensor map with 32-column x 16-row boxes, 128-byte swizzle
+int make_out_map(CUtensorMap* tm, void* ptr, const sx_gemm_args* a) {
+  PFN_encodeTiled enc = get_encode();
+  SX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t gdim[4] = {(cuuint64_t)a->N, (cuuint64_t)a->M, (cuuint64_t)a->Z0, (cuuint64_t)a->Z1};
+  cuuint64_t gstr[3];
+  gstr[0] = (cuuint64_t)a->ldc * 4;
+  gstr[1] = a->Z0 > 1 ? (cuuint64_t)a->c_stride_z0 * 4 : gstr[0] * gdim[1];
+  gstr[2] = a->Z1 > 1 ? (cuuint64_t)a->c_stride_z1 * 4 : gstr[1] * gdim[2];
+  cuuint32_t box[4] = {32, 16, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(C) failed: %d (N %d M %d ldc %lld)", (int)r, a->N, a->M,
+             (long long)a->ldc);
+  return 0;
+}
+
 template <int ES, bool A_MN, bool B_MN, bool CG2>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
+           const GemmParams& p, int grid, cudaStream_t st) {
   auto kern = sx_gemm_kernel<ES, A_MN, B_MN, CG2>;
+  constexpr int smem_bytes = CG2 ? SMEM_BYTES_CG2 : SMEM_BYTES;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   });
   SX_CHECK_CUDA(attr_err);
   if constexpr (CG2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -563,9 +626,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    SX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tp, p));
   } else {
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+    kern<<<grid, NUM_THREADS, smem_bytes, st>>>(ta, tb, tc, tp, p);
   }
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -595,6 +658,7 @@ extern "C" int sx_gemm_debug_set(const char* key, int64_t value) {
   else if (k == "dbg_epi") g_knobs.dbg_epi = value;
   else if (k == "stream_out") g_knobs.stream_out = value;
   else if (k == "cg2") g_knobs.cg2 = value;
+  else if (k == "c_tma") g_knobs.c_tma = value;
   else {
     sx_set_error("sx_gemm_debug_set: unknown key %s", key);
     return -1;
@@ -678,25 +742,43 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
   rc = make_map(&tb, a->B, es, a->N, a->K, a->Z0, a->Z1, cg2 ? BN / 2 : BN, "B");
   if (rc) return rc;
 
+  // pair kernel: fp32 outputs without atomics leave through TMA bulk stores when the layout allows it
+  CUtensorMap tc, tp;
+  memset(&tc, 0, sizeof(tc));
+  memset(&tp, 0, sizeof(tp));
+  p.c_tma = 0;
+  if (cg2 && g_knobs.c_tma != 0 && !a->accumulate && a->c_dtype == SX_F32 && a->ldc % 4 == 0 &&
+      (a->Z0 == 1 || (a->c_stride_z0 > 0 && a->c_stride_z0 % 4 == 0)) &&
+      (a->Z1 == 1 || (a->c_stride_z1 > 0 && a->c_stride_z1 % 4 == 0)) &&
+      (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 && (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0)) {
+    rc = make_out_map(&tc, a->C, a);
+    if (rc) return rc;
+    if (a->preact && a->act != SX_ACT_GELU_BWD) {
+      rc = make_out_map(&tp, a->preact, a);
+      if (rc) return rc;
+    }
+    p.c_tma = 1;
+  }
+
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (cg2) grid = 2 * (p.total_tiles < sms / 2 ? p.total_tiles : sms / 2);       // CTA pairs
   if (g_knobs.max_ctas > 0 && grid > g_knobs.max_ctas) grid = (int)g_knobs.max_ctas & (cg2 ? ~1 : ~0);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool amn = a->A.major == SX_MAJOR_MN, bmn = a->B.major == SX_MAJOR_MN;
   if (es == 4 && cg2) {
-    if (!amn && !bmn) return launch<4, false, false, true>(ta, tb, p, grid, st);
-    if (!amn && bmn) return launch<4, false, true, true>(ta, tb, p, grid, st);
-    if (amn && !bmn) return launch<4, true, false, true>(ta, tb, p, grid, st);
-    return launch<4, true, true, true>(ta, tb, p, grid, st);
+    if (!amn && !bmn) return launch<4, false, false, true>(ta, tb, tc, tp, p, grid, st);
+    if (!amn && bmn) return launch<4, false, true, true>(ta, tb, tc, tp, p, grid, st);
+    if (amn && !bmn) return launch<4, true, false, true>(ta, tb, tc, tp, p, grid, st);
+    return launch<4, true, true, true>(ta, tb, tc, tp, p, grid, st);
   } else if (es == 4) {
-    if (!amn && !bmn) return launch<4, false, false, false>(ta, tb, p, grid, st);
-    if (!amn && bmn) return launch<4, false, true, false>(ta, tb, p, grid, st);
-    if (amn && !bmn) return launch<4, true, false, false>(ta, tb, p, grid, st);
-    return launch<4, true, true, false>(ta, tb, p, grid, st);
+    if (!amn && !bmn) return launch<4, false, false, false>(ta, tb, tc, tp, p, grid, st);
+    if (!amn && bmn) return launch<4, false, true, false>(ta, tb, tc, tp, p, grid, st);
+    if (amn && !bmn) return launch<4, true, false, false>(ta, tb, tc, tp, p, grid, st);
+    return launch<4, true, true, false>(ta, tb, tc, tp, p, grid, st);
   } else {
-    if (!amn && !bmn) return launch<2, false, false, false>(ta, tb, p, grid, st);
-    if (!amn && bmn) return launch<2, false, true, false>(ta, tb, p, grid, st);
-    if (amn && !bmn) return launch<2, true, false, false>(ta, tb, p, grid, st);
-    return launch<2, true, true, false>(ta, tb, p, grid, st);
+    if (!amn && !bmn) return launch<2, false, false, false>(ta, tb, tc, tp, p, grid, st);
+    if (!amn && bmn) return launch<2, false, true, false>(ta, tb, tc, tp, p, grid, st);
+    if (amn && !bmn) return launch<2, true, false, false>(ta, tb, tc, tp, p, grid, st);
+    return launch<2, true, true, false>(ta, tb, tc, tp, p, grid, st);
   }
 }
