@@ -58,7 +58,8 @@ struct GemmParams {
   unsigned int lbo_k, sbo_k, lbo_mn_a, lbo_mn_b, sbo_mn, desc_version;
   int dbg_epi;      // bring-up: 0 normal, 1 skip global stores, 2 skip TMEM loads too
   int stream_out;   // output larger than half the L2: store with evict-first (st.global.cs), keep operands (evict-last)
-  int c_tma;        // pair kernel: C (and preact) leave through shared memory + TMA bulk stores (full 128-byte lines)
+  int c_tma;        // pair kernel: C (and preact) leave through shared memory + TMA bulk stores (full 128-byte lines);
+                    // 2 = accumulate mode: TMA reduce-add (split-K / batch-reduced gradients) instead of atomics
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
@@ -327,7 +328,8 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         sx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          sx::tma_store_4d(tm, buf, col0, row0 + 16 * P, z0, z1);
+          if (p.c_tma == 2) sx::tma_reduce_add_4d(tm, buf, col0, row0 + 16 * P, z0, z1);
+          else sx::tma_store_4d(tm, buf, col0, row0 + 16 * P, z0, z1);
           sx::tma_store_commit();
         }
         ++sbuf;
@@ -484,7 +486,7 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (col0 + 8 * j + tc + e < p.N) tmax = fmaxf(tmax, f[16 * P + 4 * j + 2 * h + e]);
               }
         }
-        if (CG2 && p.c_tma) tma_store(&tmC, f, row0, col0, z0, z1);
+        if (CG2 && p.c_tma) tma_store(&tmC, f, row0, col0, z0, p.c_sz1 == 0 ? 0 : z1);     // c_sz1 == 0: reduce over z1
         else store_frag(p.C, f, zoff, row0, col0, p.accumulate != 0);
       }
       sx::tc_fence_before();
@@ -588,11 +590,12 @@ int make_map(CUtensorMap* tm, const sx_operand& op, int es, int rows, int K, int
 int make_out_map(CUtensorMap* tm, void* ptr, const sx_gemm_args* a) {
   PFN_encodeTiled enc = get_encode();
   SX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
-  cuuint64_t gdim[4] = {(cuuint64_t)a->N, (cuuint64_t)a->M, (cuuint64_t)a->Z0, (cuuint64_t)a->Z1};
+  const bool z1_reduced = a->Z1 > 1 && a->c_stride_z1 == 0;
+  cuuint64_t gdim[4] = {(cuuint64_t)a->N, (cuuint64_t)a->M, (cuuint64_t)a->Z0, (cuuint64_t)(z1_reduced ? 1 : a->Z1)};
   cuuint64_t gstr[3];
   gstr[0] = (cuuint64_t)a->ldc * 4;
   gstr[1] = a->Z0 > 1 ? (cuuint64_t)a->c_stride_z0 * 4 : gstr[0] * gdim[1];
-  gstr[2] = a->Z1 > 1 ? (cuuint64_t)a->c_stride_z1 * 4 : gstr[1] * gdim[2];
+  gstr[2] = (a->Z1 > 1 && !z1_reduced) ? (cuuint64_t)a->c_stride_z1 * 4 : gstr[1] * gdim[2];
   cuuint32_t box[4] = {32, 16, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -747,9 +750,10 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
   memset(&tc, 0, sizeof(tc));
   memset(&tp, 0, sizeof(tp));
   p.c_tma = 0;
-  if (cg2 && g_knobs.c_tma != 0 && !a->accumulate && a->c_dtype == SX_F32 && a->ldc % 4 == 0 &&
+  const bool z1_reduced = a->accumulate && a->Z1 > 1 && a->c_stride_z1 == 0;        // all z1 slices add into one output
+  if (cg2 && g_knobs.c_tma != 0 && a->c_dtype == SX_F32 && a->ldc % 4 == 0 &&
       (a->Z0 == 1 || (a->c_stride_z0 > 0 && a->c_stride_z0 % 4 == 0)) &&
-      (a->Z1 == 1 || (a->c_stride_z1 > 0 && a->c_stride_z1 % 4 == 0)) &&
+      (a->Z1 == 1 || z1_reduced || (a->c_stride_z1 > 0 && a->c_stride_z1 % 4 == 0)) &&
       (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 && (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0)) {
     rc = make_out_map(&tc, a->C, a);
     if (rc) return rc;
@@ -757,7 +761,7 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
       rc = make_out_map(&tp, a->preact, a);
       if (rc) return rc;
     }
-    p.c_tma = 1;
+    p.c_tma = a->accumulate ? 2 : 1;
   }
 
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
