@@ -63,7 +63,7 @@ def _sink_or_zeros(p, like=None):
     tgt = _grad_target(p)
     if tgt is not None:
         return tgt, None
-    z = torch.zeros_like(p if like is None else like)
+    z = _zeros_like(p if like is None else like)
     return z, z
 
 
@@ -101,6 +101,7 @@ def reseed(seed: int, device=None):
 def advance_seed(device):
     """Bump the base seed once per training step (captured into CUDA graphs like any other kernel)."""
     L.call("sx_seed_advance", _base_seed(device).data_ptr(), 0xD1B54A32D192ED03, _stream())
+    _begin_zero_arena(device)                   # step boundary: one memset for all zero-initialised scratch of the step
 
 
 def new_dropout_seed(device) -> torch.Tensor:
@@ -131,6 +132,45 @@ def _req_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
             raise L.SxError("segtran_b200 ops need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# zero-initialised scratch (accumulation targets of split-K / batch-reduced GEMMs and column sums): instead of one tiny
+# fill kernel per buffer (~40 per training step), every request of a step is carved out of ONE arena that a single
+# memset clears.  A new arena tensor is allocated at each step boundary (advance_seed), sized by the largest step seen so
+# far; slices keep their arena alive, so nothing is ever recycled under a live tensor.  Outside of training steps (or on
+# the first step) requests fall back to torch.zeros.
+# ------------------------------------------------------------------------------------------------
+_zero_arena = {}
+
+
+def _arena_state(device):
+    return _zero_arena.setdefault((device.type, device.index), {"buf": None, "off": 0, "peak": 0})
+
+
+def _begin_zero_arena(device):
+    st = _arena_state(device)
+    st["peak"] = max(st["peak"], st["off"])
+    st["off"] = 0
+    st["buf"] = torch.zeros(st["peak"], device=device, dtype=torch.float32) if st["peak"] else None
+
+
+def _zeros(shape, device) -> torch.Tensor:
+    if isinstance(shape, int):
+        shape = (shape,)
+    n = 1
+    for d in shape:
+        n *= int(d)
+    st = _arena_state(device)
+    off, n_al = st["off"], (n + 63) // 64 * 64           # 256-byte slots (TMA / vector accesses stay legal)
+    st["off"] = off + n_al
+    if st["buf"] is not None and off + n_al <= st["buf"].numel():
+        return st["buf"][off:off + n].view(tuple(shape))
+    return torch.zeros(tuple(shape), device=device, dtype=torch.float32)
+
+
+def _zeros_like(t: torch.Tensor) -> torch.Tensor:
+    return _zeros(tuple(t.shape), t.device)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -208,8 +248,10 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
     if split_k is None:
         split_k = _pick_split_k(M, N, K, Z0 * Z1) if (linear_epi and (fresh or accumulate or reduce_z1)) else 1
     if fresh:
-        alloc = torch.zeros if (accumulate or reduce_z1 or split_k > 1) else torch.empty
-        out = alloc((oz1, Z0, M, N), device=a.device, dtype=torch.float32)
+        if accumulate or reduce_z1 or split_k > 1:
+            out = _zeros((oz1, Z0, M, N), a.device)
+        else:
+            out = torch.empty((oz1, Z0, M, N), device=a.device, dtype=torch.float32)
     o4 = _as4(out)
     if o4.shape[-2:] != (M, N) or o4.stride(-1) != 1:
         raise L.SxError("gemm_nt: bad output view %s %s" % (tuple(o4.shape), o4.stride()))
@@ -343,7 +385,7 @@ def round_tf32(x: torch.Tensor) -> torch.Tensor:
 def colsum(x2d: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[c] += sum_r x2d[r, c] (rows uniformly strided)."""
     if out is None:
-        out = torch.zeros(x2d.shape[1], device=x2d.device, dtype=torch.float32)
+        out = _zeros((x2d.shape[1],), x2d.device)
     L.call("sx_colsum", x2d.data_ptr(), L.SX_F32, x2d.shape[0], x2d.shape[1], x2d.stride(0), out.data_ptr(), _stream())
     return out
 
@@ -437,7 +479,7 @@ class _AttnScores(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # dQ[b,m] (U1 x d) = scale * dS[b,m] (U1 x U2) . K[b,m] (U2 x d)
             bcast = Bq == 1 and B > 1
-            dq = torch.zeros_like(q) if bcast else torch.empty_like(q)
+            dq = _zeros_like(q) if bcast else torch.empty_like(q)
             gemm_nt(dS, k.view(B, U2, M, d).permute(0, 2, 3, 1), out=dq.view(Bq, U1, M, d).permute(0, 2, 1, 3),
                     alpha=scale, round_out=False, reduce_z1=bcast, split_k=1)
         if ctx.needs_input_grad[1]:
@@ -445,7 +487,7 @@ class _AttnScores(torch.autograd.Function):
             gemm_nt(dS.transpose(-1, -2), q.view(Bq, U1, M, d).permute(0, 2, 3, 1),
                     out=dk.view(B, U2, M, d).permute(0, 2, 1, 3), alpha=scale, round_out=False)
         if rb_shape is not None and ctx.needs_input_grad[4]:
-            drb = torch.zeros(U1, device=q.device, dtype=torch.float32)     # sum over batch and keys
+            drb = _zeros((U1,), q.device)     # sum over batch and keys
             L.call("sx_rowsum", dS.data_ptr(), B * U1, U2, dS.stride(-2), U1, drb.data_ptr(), _stream())
             drb = drb.view(rb_shape)
         return dq, dk, None, None, drb
@@ -721,7 +763,7 @@ class _AttnPVGeluGroupLinear(torch.autograd.Function):
                 dW = gemm_nt(dY.transpose(-1, -2), G.transpose(-1, -2), reduce_z1=True, round_out=False).view(wshape)
         if ctx.needs_input_grad[7]:
             tgt = _grad_target(bo)
-            dbo_buf = tgt if tgt is not None else torch.zeros((M * Fd,), device=G.device, dtype=torch.float32)
+            dbo_buf = tgt if tgt is not None else _zeros((M * Fd,), G.device)
             L.call("sx_colsum_batched", dY.data_ptr(), B, M * U1 * Fd, M, U1 * Fd, U1, Fd, Fd, dbo_buf.data_ptr(), _stream())
             dbo = None if tgt is not None else dbo_buf
         if ctx.needs_input_grad[0]:
@@ -807,7 +849,7 @@ class _GroupLinear(torch.autograd.Function):
                 dW = dW.view(ctx.wshape)
         if ctx.needs_input_grad[2]:
             tgt = _grad_target(bo)
-            db = tgt if tgt is not None else torch.zeros((M * Fd,), device=G.device, dtype=torch.float32)
+            db = tgt if tgt is not None else _zeros((M * Fd,), G.device)
             L.call("sx_colsum_batched", dY.data_ptr(), B, M * N * Fd, M, N * Fd, N, Fd, Fd, db.data_ptr(), _stream())
             if tgt is not None:
                 db = None
@@ -910,7 +952,7 @@ class _Prologue(torch.autograd.Function):
         dx = torch.empty_like(x)
         dgb, dg = _sink_or_zeros(ctx.leaves[0])
         dbb, db = _sink_or_zeros(ctx.leaves[1])
-        dpe = torch.zeros_like(pe) if ctx.needs_input_grad[3] else None
+        dpe = _zeros_like(pe) if ctx.needs_input_grad[3] else None
         scratch = torch.empty_like(x)
         L.call("sx_prologue_bwd", dh.data_ptr(), x.data_ptr(), B, N, Cd, g.data_ptr(), b.data_ptr(), pe.data_ptr(), C0,
                pe_bstride, posw, _ptr(mask), drop_p, *_seed_args(seed), stats.data_ptr(), dx.data_ptr(), dgb.data_ptr(), dbb.data_ptr(),
@@ -940,7 +982,7 @@ class _Dot(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w):
         x = x.contiguous()
-        out = torch.zeros(1, device=x.device, dtype=torch.float32)
+        out = _zeros((1,), x.device)
         L.call("sx_dot", x.data_ptr(), w.data_ptr(), x.numel(), out.data_ptr(), _stream())
         ctx.save_for_backward(w)
         ctx.shape = x.shape
@@ -1116,7 +1158,7 @@ class _HeadContract(torch.autograd.Function):
         # dWcb[k,c] = sum_{b,v} dL[b,k,v] curr[b,c,v]: a (K x Cf x B*V) product streamed once through the tensor
         # cores (TF32 operands, fp32 accumulation; HBM-bound on reading curr), reduced over the batch atomically
         dWcb = gemm_nt(dL.view(B, 1, K, V), curr.view(B, 1, Cf, V), reduce_z1=True, round_out=False).view(K, Cf)
-        dcc = torch.zeros(K, device=curr.device, dtype=torch.float32)               # d(const)[k] = sum_{b,v} dL
+        dcc = _zeros((K,), curr.device)               # d(const)[k] = sum_{b,v} dL
         L.call("sx_rowsum", dL.data_ptr(), B * K, V, V, K, dcc.data_ptr(), _stream())
         if Wb2 is not None:
             # Wcb = Wc Wb ; cc = Wc bb + bc
@@ -1165,7 +1207,7 @@ class _TokenClassScores(torch.autograd.Function):
             dWc = gemm_nt(dt.view(B, 1, K, N), vf.transpose(1, 2).unsqueeze(1), reduce_z1=True, round_out=False)
             dWc = dWc.view(K, Fd)
         else:
-            dWc = torch.zeros((1, K, Fd), device=vf.device, dtype=torch.float32)
+            dWc = _zeros((1, K, Fd), vf.device)
             for bi in range(B):
                 _sgemm(dt[bi], vf[bi], K, Fd, N, (N, 1), (Fd, 1), out=dWc, accumulate=True)
             dWc = dWc[0]
