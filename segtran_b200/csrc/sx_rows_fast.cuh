@@ -46,6 +46,20 @@ __device__ __forceinline__ float4 drop4(float4 v, float p, float scale, unsigned
   v.w = sx::drop_keep(h, 3, p16) ? v.w * scale : 0.f;
   return v;
 }
+// keep bits of one float4 group (bit j = element j is kept) and their application: the two-pass row kernels hash each
+// group once and park the bits in shared memory instead of re-hashing in every pass
+__device__ __forceinline__ uint32_t keep4(unsigned long long seed, unsigned long long idx, uint32_t p16) {
+  const uint2 h = sx::drop_hash(seed, idx >> 2);
+  return (sx::drop_keep(h, 0, p16) ? 1u : 0u) | (sx::drop_keep(h, 1, p16) ? 2u : 0u) |
+         (sx::drop_keep(h, 2, p16) ? 4u : 0u) | (sx::drop_keep(h, 3, p16) ? 8u : 0u);
+}
+__device__ __forceinline__ float4 mask4(float4 v, uint32_t bits, float scale) {
+  v.x = (bits & 1u) ? v.x * scale : 0.f;
+  v.y = (bits & 2u) ? v.y * scale : 0.f;
+  v.z = (bits & 4u) ? v.z * scale : 0.f;
+  v.w = (bits & 8u) ? v.w * scale : 0.f;
+  return v;
+}
 __device__ __forceinline__ float4 rnd4(float4 v, int rnd) {
   if (rnd) { v.x = sx::round_tf32(v.x); v.y = sx::round_tf32(v.y); v.z = sx::round_tf32(v.z); v.w = sx::round_tf32(v.w); }
   return v;
@@ -65,8 +79,10 @@ ln_softaggr_fwd_fast(const float* __restrict__ Y, int B, int M, int N, int F, co
                      float* __restrict__ out, float* __restrict__ stats, float* __restrict__ wts) {
   seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   __shared__ float s_sc[FAST_WARPS][MAX_MODES], s_mu[FAST_WARPS][MAX_MODES], s_rs[FAST_WARPS][MAX_MODES];
+  __shared__ uint32_t s_keep[FAST_WARPS][MAX_MODES][(NV + 7) / 8][32];      // dropout keep bits of pass 1, reused in pass 2
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const uint32_t p16 = sx::drop_p16(drop_p);
   const long long T_ = (long long)B * N;
   for (long long t = (long long)blockIdx.x * FAST_WARPS + warp; t < T_; t += (long long)gridDim.x * FAST_WARPS) {
     const long long bi = t / N, ni = t % N;
@@ -77,10 +93,18 @@ ln_softaggr_fwd_fast(const float* __restrict__ Y, int B, int M, int N, int F, co
       float4 v[NV];
       row_load<NV>(v, Y + ro * F, F, lane);
       if (drop_p > 0.f) {
+        uint32_t kb[(NV + 7) / 8];
+#pragma unroll
+        for (int w = 0; w < (NV + 7) / 8; ++w) kb[w] = 0u;
 #pragma unroll
         for (int i = 0; i < NV; ++i)
-          if (4 * lane + 128 * i < F)
-            v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + 4 * lane + 128 * i));
+          if (4 * lane + 128 * i < F) {
+            const uint32_t bits = keep4(seed, (unsigned long long)(ro * F + 4 * lane + 128 * i), p16);
+            kb[i >> 3] |= bits << (4 * (i & 7));
+            v[i] = mask4(v[i], bits, keep_scale);
+          }
+#pragma unroll
+        for (int w = 0; w < (NV + 7) / 8; ++w) s_keep[warp][m][w][lane] = kb[w];
       }
       float mean, rstd;
       row_mean_rstd<NV>(v, F, lane, mean, rstd);
@@ -124,7 +148,7 @@ ln_softaggr_fwd_fast(const float* __restrict__ Y, int B, int M, int N, int F, co
       for (int i = 0; i < NV; ++i) {
         const int c = 4 * lane + 128 * i;
         if (c < F) {
-          if (drop_p > 0.f) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
+          if (drop_p > 0.f) v[i] = mask4(v[i], s_keep[warp][m][i >> 3][lane] >> (4 * (i & 7)), keep_scale);
           const float4 gg = ld4(g + c), bb = ld4(b + c);
           o[i].x += w * ((v[i].x - mean) * rstd * gg.x + bb.x);
           o[i].y += w * ((v[i].y - mean) * rstd * gg.y + bb.y);
@@ -150,6 +174,7 @@ ln_softaggr_bwd_rows_fast(const float* __restrict__ dout, const float* __restric
                           float* __restrict__ dscore_out, float* __restrict__ dbs, int rnd) {
   seed += seed_dev ? *seed_dev : 0ull;      // per-call device seed (CUDA-graph safe)
   __shared__ float s_dw[FAST_WARPS][MAX_MODES], s_w[FAST_WARPS][MAX_MODES];
+  __shared__ uint32_t s_keep[FAST_WARPS][MAX_MODES][(NV + 7) / 8][32];      // dropout keep bits: hashed once, used 3 times
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const uint32_t p16 = sx::drop_p16(drop_p);
@@ -166,17 +191,28 @@ ln_softaggr_bwd_rows_fast(const float* __restrict__ dout, const float* __restric
       float4 v[NV];
       row_load<NV>(v, Y + ro * F, F, lane);
       float dot = 0.f;
+      uint32_t kb[(NV + 7) / 8];
+#pragma unroll
+      for (int w = 0; w < (NV + 7) / 8; ++w) kb[w] = 0u;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = 4 * lane + 128 * i;
         if (c < F) {
-          if (drop_p > 0.f) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
+          if (drop_p > 0.f) {
+            const uint32_t bits = keep4(seed, (unsigned long long)(ro * F + c), p16);
+            kb[i >> 3] |= bits << (4 * (i & 7));
+            v[i] = mask4(v[i], bits, keep_scale);
+          }
           const float4 gg = ld4(g + c), bb = ld4(b + c);
           dot += go[i].x * ((v[i].x - mean) * rstd * gg.x + bb.x) + go[i].y * ((v[i].y - mean) * rstd * gg.y + bb.y) +
                  go[i].z * ((v[i].z - mean) * rstd * gg.z + bb.z) + go[i].w * ((v[i].w - mean) * rstd * gg.w + bb.w);
         }
       }
       dot = sx::warp_sum(dot);
+      if (drop_p > 0.f) {
+#pragma unroll
+        for (int w = 0; w < (NV + 7) / 8; ++w) s_keep[warp][m][w][lane] = kb[w];
+      }
       if (lane == 0) { s_dw[warp][m] = dot; s_w[warp][m] = wts[(bi * M + m) * N + ni]; }
     }
     __syncwarp();
@@ -198,7 +234,7 @@ ln_softaggr_bwd_rows_fast(const float* __restrict__ dout, const float* __restric
       for (int i = 0; i < NV; ++i) {
         const int c = 4 * lane + 128 * i;
         if (c < F) {
-          if (drop_p > 0.f) v[i] = drop4(v[i], drop_p, keep_scale, seed, (unsigned long long)(ro * F + c));
+          if (drop_p > 0.f) v[i] = mask4(v[i], s_keep[warp][m][i >> 3][lane] >> (4 * (i & 7)), keep_scale);
           const float4 gg = ld4(g + c), ww = ld4(ws + c);
           v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
           v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
@@ -219,11 +255,7 @@ ln_softaggr_bwd_rows_fast(const float* __restrict__ dout, const float* __restric
           r.y = rstd * ((wm * go[i].y + dscore * ww.y) * gg.y - s1 - v[i].y * s2);
           r.z = rstd * ((wm * go[i].z + dscore * ww.z) * gg.z - s1 - v[i].z * s2);
           r.w = rstd * ((wm * go[i].w + dscore * ww.w) * gg.w - s1 - v[i].w * s2);
-          if (drop_p > 0.f) {
-            const uint2 h = sx::drop_hash(seed, (unsigned long long)(ro * F + c) >> 2);
-            r.x = sx::drop_keep(h, 0, p16) ? r.x * keep_scale : 0.f; r.y = sx::drop_keep(h, 1, p16) ? r.y * keep_scale : 0.f;
-            r.z = sx::drop_keep(h, 2, p16) ? r.z * keep_scale : 0.f; r.w = sx::drop_keep(h, 3, p16) ? r.w * keep_scale : 0.f;
-          }
+          if (drop_p > 0.f) r = mask4(r, s_keep[warp][m][i >> 3][lane] >> (4 * (i & 7)), keep_scale);
           *reinterpret_cast<float4*>(dY + ro * F + c) = rnd4(r, rnd);
         }
       }
