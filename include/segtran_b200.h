@@ -194,6 +194,19 @@ int sx_token_scores(const float* vf, const float* W, int32_t B, int32_t N, int32
 int sx_token_scores_bwd(const float* dt, const float* W, int32_t B, int32_t N, int32_t F, int32_t K, float* dvf,
                         void* stream);
 /* -------------------------------------------------------------------------------------------
+ * FPN pyramid stage (segtran3d.py:299-313, :347-359, segtran2d.py:244-300):
+ *   curr <- GroupNorm_G( conv1x1(curr) + bias + upsample(higher) )
+ * conv1x1 + bias + add is ONE sx_gemm launch on the channels-first tensors (A = W [Cout x Cin] broadcast over the batch,
+ * B = x[b] read as an MN-major [V x Cin] operand, bias mode SX_BIAS_M, addend = the upsampled level); the upsampling is
+ * sx_resize_axis_fwd per axis; GroupNorm is below.  x, y, dy, dx: [B, C, V] fp32.  csum: [B*C*2] double workspace,
+ * stats: [B*G*2] (mean, rstd) kept for the backward, coef: [B*G*2] workspace.  dgamma/dbeta are accumulated into.
+ * ------------------------------------------------------------------------------------------- */
+int sx_groupnorm_fwd(const float* x, int32_t B, int32_t C, int64_t V, int32_t G, const float* gamma, const float* beta,
+                     float eps, double* csum, float* stats, float* y, int32_t round_tf32, void* stream);
+int sx_groupnorm_bwd(const float* dy, const float* x, int32_t B, int32_t C, int64_t V, int32_t G, const float* gamma,
+                     const float* stats, double* csum, float* coef, float* dx, float* dgamma, float* dbeta, void* stream);
+
+/* -------------------------------------------------------------------------------------------
  * Training-step tail: segmentation loss and BertAdam on flat buckets.
  * Everything the step needs (loss scalars, clip coefficients, scheduled learning rates, the step
  * counter) is produced and consumed on the device, so the step can be captured in a CUDA graph.

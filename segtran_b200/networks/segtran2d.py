@@ -176,11 +176,18 @@ class Segtran2d(SegtranInitWeights):
 
     @staticmethod
     def _pyramid(feats, layers, convs, norms, scheme, start):
+        """conv1x1(curr) (+) bilinear(higher) -> norm, bottom-up over `layers` (reference segtran3d.py:299-313, :347-359 /
+        segtran2d.py:244-257, :286-300).  On CUDA with GroupNorm and TMA-legal shapes each stage is the fused
+        ops.fpn_stage (conv + bias + add in one tcgen05 GEMM, two-pass GroupNorm); otherwise the stock modules run."""
         cur = feats[start]
         for layer in layers:
-            up = convs[layer](cur)
+            conv, norm = convs[layer], norms[layer + 1]
+            if isinstance(norm, nn.GroupNorm) and ops.conv1x1_ok(cur, conv) and ops.fpn_fusion_enabled():
+                cur = ops.fpn_stage(cur, feats[layer + 1], conv, norm, scheme)
+                continue
+            up = conv(cur)
             hi = F.interpolate(feats[layer + 1], size=up.shape[2:], mode='bilinear', align_corners=False)
-            cur = norms[layer + 1](up + hi) if scheme == 'AN' else norms[layer + 1](up) + hi
+            cur = norm(up + hi) if scheme == 'AN' else norm(up) + hi
         return cur
 
     def _backbone_feats(self, batch):
@@ -240,7 +247,11 @@ class Segtran2d(SegtranInitWeights):
         feats = self._backbone_feats(batch)
         cur = self._pyramid(feats, self.in_fpn_layers[:-1], self.in_fpn_convs, self.in_fpn_norms, self.in_fpn_scheme,
                             self.in_fpn_layers[0])
-        feat_fpn = self.in_fpn_bridgeconv(cur)
+        bc = self.in_fpn_bridgeconv
+        if isinstance(bc, nn.Conv2d) and ops.conv1x1_ok(cur, bc) and ops.fpn_fusion_enabled():
+            feat_fpn = ops.conv1x1_add(cur, bc.weight, bc.bias)          # 1x1 bridge conv as one GEMM
+        else:
+            feat_fpn = bc(cur)
         self.feature_maps.append(feat_fpn)
         layers = self.out_fpn_layers[:-len(self.in_fpn_layers)]
         curr_feat = self._pyramid(feats, layers, self.out_fpn_convs, self.out_fpn_norms, self.out_fpn_scheme,

@@ -198,19 +198,29 @@ class Segtran3d(SegtranInitWeights):
 
     @staticmethod
     def _pyramid(feats, layers, convs, norms, scheme, start):
-        """conv1x1(curr) (+) trilinear(higher) -> norm, bottom-up over `layers` (reference :299-313, :347-359)."""
+        """conv1x1(curr) (+) trilinear(higher) -> norm, bottom-up over `layers` (reference segtran3d.py:299-313, :347-359 /
+        segtran2d.py:244-257, :286-300).  On CUDA with GroupNorm and TMA-legal shapes each stage is the fused
+        ops.fpn_stage (conv + bias + add in one tcgen05 GEMM, two-pass GroupNorm); otherwise the stock modules run."""
         cur = feats[start]
         for layer in layers:
-            up = convs[layer](cur)
+            conv, norm = convs[layer], norms[layer + 1]
+            if isinstance(norm, nn.GroupNorm) and ops.conv1x1_ok(cur, conv) and ops.fpn_fusion_enabled():
+                cur = ops.fpn_stage(cur, feats[layer + 1], conv, norm, scheme)
+                continue
+            up = conv(cur)
             hi = F.interpolate(feats[layer + 1], size=up.shape[2:], mode='trilinear', align_corners=False)
-            cur = norms[layer + 1](up + hi) if scheme == 'AN' else norms[layer + 1](up) + hi
+            cur = norm(up + hi) if scheme == 'AN' else norm(up) + hi
         return cur
 
     def in_fpn_forward(self, batch_base_feats, nonzero_mask):
         """In-FPN pyramid + depth pooling (stock ops): -> feat_fpn [B,C0,D2,H2,W2], vmask [B,N]."""
         cur = self._pyramid(batch_base_feats, self.in_fpn_layers[:-1], self.in_fpn_convs, self.in_fpn_norms,
                             self.in_fpn_scheme, self.in_fpn_layers[0])
-        cur = self.in_fpn_bridgeconv(cur)
+        bc = self.in_fpn_bridgeconv
+        if isinstance(bc, nn.Conv3d) and ops.conv1x1_ok(cur, bc) and ops.fpn_fusion_enabled():
+            cur = ops.conv1x1_add(cur, bc.weight, bc.bias)               # 1x1x1 bridge conv as one GEMM
+        else:
+            cur = bc(cur)
         size = list(cur.shape[2:])
         size[0] //= self.D_pool_K
         cur = F.interpolate(cur, size=size, mode='trilinear', align_corners=False)

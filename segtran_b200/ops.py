@@ -290,6 +290,8 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
     g.drop_p = drop_p
     g.drop_seed, g.drop_seed_dev = _seed_args(seed)
     if addend is not None:
+        if addend.dtype != torch.float32 or tuple(addend.shape[-2:]) != (M, N) or _as4(addend).stride() != o4.stride():
+            raise L.SxError("gemm_nt: addend must be an fp32 tensor in the output's layout")
         g.addend = addend.data_ptr()
     L.call("sx_gemm", C.byref(g), _stream())
     return out
@@ -312,13 +314,14 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = N
             bias: Optional[torch.Tensor] = None, bias_mode: int = L.SX_BIAS_N, gelu: bool = False,
             preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
             amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
-            reduce_z1: bool = False, gelu_bwd: Optional[torch.Tensor] = None) -> torch.Tensor:
+            reduce_z1: bool = False, gelu_bwd: Optional[torch.Tensor] = None,
+            addend: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C[..., m, n] = epilogue(alpha * sum_k a[..., m, k] b[..., n, k]) on the tcgen05 GEMM.  In the default
     precision this is one launch; in 'tf32x3' it is three passes on the hi/lo operand splits."""
     if _PRECISION == "tf32":
         return _gemm_nt_1(a, b, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
                           accumulate=accumulate, split_k=split_k, amax=amax, drop_p=drop_p, seed=seed,
-                          round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd)
+                          round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd, addend=addend)
     _req_cuda(a, b)
     ah, al = _tf32_split(a)
     bh, bl = _tf32_split(b)
@@ -334,7 +337,7 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = N
                           device=a.device, dtype=torch.float32)
     o4 = _as4(out)
     part = torch.empty_strided(o4.size(), o4.stride(), device=a.device, dtype=torch.float32)    # C's layout
-    _gemm_nt_1(al, bh, out=part, alpha=alpha, split_k=1, round_out=False)
+    _gemm_nt_1(al, bh, out=part, alpha=alpha, split_k=1, round_out=False, addend=addend)
     _gemm_nt_1(ah, bl, out=part, alpha=alpha, split_k=1, round_out=False, addend=part)
     return _gemm_nt_1(ah, bh, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
                       split_k=1, amax=amax, drop_p=drop_p, seed=seed, round_out=False, addend=part, gelu_bwd=gelu_bwd)
@@ -1212,6 +1215,141 @@ class _TokenClassScores(torch.autograd.Function):
                 _sgemm(dt[bi], vf[bi], K, Fd, N, (N, 1), (Fd, 1), out=dWc, accumulate=True)
             dWc = dWc[0]
         return dvf, dWc
+
+
+# ------------------------------------------------------------------------------------------------
+# FPN pyramid stage: curr <- GroupNorm(conv1x1(curr) + upsample(higher))   on channels-first tensors
+# ------------------------------------------------------------------------------------------------
+class _Conv1x1Add(torch.autograd.Function):
+    """y[b] = W x[b] + bias (+ addend[b]) for channels-first x [B,Cin,V]: a 1x1(x1) convolution with the "add the
+    upsampled coarser level" of an FPN stage in its epilogue (segtran3d.py:300-306, :348-354).  One GEMM: W is the K-major
+    A operand broadcast over the batch, x[b] is read in place as an MN-major [V x Cin] operand."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, addend):
+        B, Cin, V = x.shape
+        Cout = W.shape[0]
+        xr = round_tf32(x)                                   # the level below comes from outside (backbone): round once
+        Wr = round_tf32(W.reshape(Cout, Cin))
+        y = torch.empty((B, 1, Cout, V), device=x.device, dtype=torch.float32)
+        ad = None if addend is None else addend.contiguous().view(B, 1, Cout, V)
+        gemm_nt(Wr.view(1, 1, Cout, Cin), xr.view(B, 1, Cin, V).transpose(-1, -2), out=y, bias=b, bias_mode=L.SX_BIAS_M,
+                addend=ad, round_out=False)
+        ctx.save_for_backward(xr, Wr)
+        ctx.meta = (W.shape, b is not None, addend is not None)
+        ctx.leaves = (W, b)
+        return y.view(B, Cout, V)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xr, Wr = ctx.saved_tensors
+        wshape, has_b, has_add = ctx.meta
+        W, b = ctx.leaves
+        B, Cin, V = xr.shape
+        Cout = Wr.shape[0]
+        dy = dy.contiguous()
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_nt(Wr.t().view(1, 1, Cin, Cout), dy.view(B, 1, Cout, V).transpose(-1, -2), round_out=False)
+            dx = dx.view(B, Cin, V)
+        if ctx.needs_input_grad[1]:
+            tgt = _grad_target(W)
+            if tgt is not None:
+                gemm_nt(dy.view(B, 1, Cout, V), xr.view(B, 1, Cin, V), out=tgt.view(1, 1, Cout, Cin), reduce_z1=True,
+                        accumulate=True, round_out=False)
+            else:
+                dW = gemm_nt(dy.view(B, 1, Cout, V), xr.view(B, 1, Cin, V), reduce_z1=True, round_out=False).view(wshape)
+        if has_b and ctx.needs_input_grad[2]:
+            tgt = _grad_target(b)
+            buf = tgt if tgt is not None else _zeros((Cout,), dy.device)
+            L.call("sx_rowsum", dy.data_ptr(), B * Cout, V, V, Cout, buf.data_ptr(), _stream())
+            db = None if tgt is not None else buf
+        return dx, dW, db, (dy if has_add else None)
+
+
+class _GroupNorm(torch.autograd.Function):
+    """nn.GroupNorm(G, C) on channels-first [B,C,V] (segtran3d.py:150, :174; eps 1e-5): one reduction pass + one apply pass."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, G, eps, round_out):
+        x = x.contiguous()
+        B, Cd, V = x.shape
+        y = torch.empty_like(x)
+        csum = torch.empty(B * Cd * 2, device=x.device, dtype=torch.float64)
+        stats = torch.empty(B * G * 2, device=x.device, dtype=torch.float32)
+        L.call("sx_groupnorm_fwd", x.data_ptr(), B, Cd, V, G, _ptr(gamma), _ptr(beta), float(eps), csum.data_ptr(),
+               stats.data_ptr(), y.data_ptr(), _rt() if round_out else 0, _stream())
+        ctx.save_for_backward(x, gamma, stats)
+        ctx.meta = (G,)
+        ctx.leaves = (gamma, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, stats = ctx.saved_tensors
+        (G,) = ctx.meta
+        B, Cd, V = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        csum = torch.empty(B * Cd * 2, device=x.device, dtype=torch.float64)
+        coef = torch.empty(B * G * 2, device=x.device, dtype=torch.float32)
+        dg = db = dgb = dbb = None
+        if gamma is not None:
+            dgb, dg = _sink_or_zeros(ctx.leaves[0])
+            dbb, db = _sink_or_zeros(ctx.leaves[1])
+        L.call("sx_groupnorm_bwd", dy.data_ptr(), x.data_ptr(), B, Cd, V, G, _ptr(gamma), stats.data_ptr(), csum.data_ptr(),
+               coef.data_ptr(), dx.data_ptr(), _ptr(dgb), _ptr(dbb), _stream())
+        return dx, dg, db, None, None, None
+
+
+def conv1x1_add(x, W, b=None, addend=None):
+    """x [B,Cin,*sp] -> [B,Cout,*sp]: 1x1(x1) convolution (+ bias) (+ addend of the output's shape)."""
+    sp = x.shape[2:]
+    B, Cin = x.shape[:2]
+    y = _Conv1x1Add.apply(x.reshape(B, Cin, -1), W, b, None if addend is None else addend.reshape(B, W.shape[0], -1))
+    return y.view(B, W.shape[0], *sp)
+
+
+def group_norm(x, gamma, beta, num_groups, eps=1e-5, round_out=False):
+    sp = x.shape
+    return _GroupNorm.apply(x.reshape(sp[0], sp[1], -1), gamma, beta, int(num_groups), float(eps), round_out).view(sp)
+
+
+_FPN_FUSION = True
+
+
+def set_fpn_fusion(on: bool):
+    """Switch the fused FPN pyramid stages (conv1x1 + add GEMM, GroupNorm kernels) on or off (off = stock PyTorch modules)."""
+    global _FPN_FUSION
+    _FPN_FUSION = bool(on)
+
+
+def fpn_fusion_enabled() -> bool:
+    return _FPN_FUSION
+
+
+def conv1x1_ok(x, conv) -> bool:
+    """Whether the tensor-core path can take this 1x1 convolution: TMA needs 16-byte pitches on both operands."""
+    V = 1
+    for d in x.shape[2:]:
+        V *= int(d)
+    k = conv.kernel_size
+    return x.is_cuda and x.dtype == torch.float32 and all(int(t) == 1 for t in k) and conv.groups == 1 and \
+        all(int(t) == 1 for t in conv.stride) and all(int(t) == 0 for t in conv.padding) and \
+        V % 4 == 0 and conv.in_channels % 4 == 0
+
+
+def fpn_stage(cur, higher, conv, norm, scheme="AN"):
+    """One bottom-up FPN stage (segtran3d.py:299-313 / :347-359, segtran2d.py:244-257 / :286-300):
+        'AN': norm(conv(cur) + upsample(higher))        otherwise: norm(conv(cur)) + upsample(higher)
+    conv: nn.Conv2d/3d with a 1x1(x1) kernel, norm: nn.GroupNorm.  The upsampled level is the GEMM epilogue's addend."""
+    up_size = tuple(cur.shape[2:])
+    hi = higher if tuple(higher.shape[2:]) == up_size else resize_linear(higher, up_size)
+    if scheme == 'AN':
+        y = conv1x1_add(cur, conv.weight, conv.bias, addend=hi)
+        return group_norm(y, norm.weight, norm.bias, norm.num_groups, norm.eps)
+    y = conv1x1_add(cur, conv.weight, conv.bias)
+    return _Add.apply(group_norm(y, norm.weight, norm.bias, norm.num_groups, norm.eps), hi)
 
 
 def seg_head(curr, vfeat_fused, grid, Wb, bb, Wc, bc, out_size, d_pool_k=1, permute_dhw_to_hwd=False):
