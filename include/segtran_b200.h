@@ -88,6 +88,8 @@ typedef struct {
   const uint64_t* drop_seed_dev; /* optional device seed added to drop_seed (CUDA-graph safe) */
   const float* addend;           /* optional fp32 tensor in C's layout: C = epilogue(alpha*A.B^T + addend); used by the
                                     error-compensated 3-pass TF32 mode (A_hi B_hi + A_lo B_hi + A_hi B_lo) */
+  float* colsum;                 /* optional [N] fp32: += column sums of the stored values over all rows and batch slices
+                                    (a bias gradient that would otherwise need its own pass over the output) */
 } sx_gemm_args;
 
 int sx_gemm(const sx_gemm_args* args, void* stream);
@@ -224,9 +226,10 @@ int sx_seg_loss_bwd(const float* logits, const float* mask, int32_t B, int32_t K
  * ONE parameter each): seg_param / seg_off / seg_len [nseg].  lr, wd: per-parameter [P].  schedule: SX_SCHED_*; t_total = -1
  * disables the schedule.  step: device counter (read, then incremented).  sumsq [P] double, coef [P], lr_eff [P]: device
  * workspaces.  total_norm: optional device float (the pre-clip global norm).  A parameter whose gradient is exactly zero is
- * left untouched (the reference skips p.grad is None: never-used parameters). */
+ * left untouched (the reference skips p.grad is None: never-used parameters).  p_tf32 (optional): a second parameter
+ * buffer that receives the TF32-rounded new values, so the next forward needs no per-weight rounding pass. */
 enum { SX_SCHED_WARMUP_LINEAR = 0, SX_SCHED_WARMUP_CONSTANT = 1 };
-int sx_adam_step(float* p, const float* g, float* m, float* v, const int32_t* seg_param, const int64_t* seg_off,
+int sx_adam_step(float* p, float* p_tf32, const float* g, float* m, float* v, const int32_t* seg_param, const int64_t* seg_off,
                  const int32_t* seg_len, int32_t nseg, int32_t P, const float* lr, const float* wd, double b1, double b2,
                  double eps, float grad_clip, float max_grad_norm, float warmup, int64_t t_total, int32_t schedule,
                  int64_t* step, double* sumsq, float* coef, float* lr_eff, float* total_norm, void* stream);

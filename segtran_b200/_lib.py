@@ -35,7 +35,7 @@ class sx_gemm_args(C.Structure):
                 ("alpha", C.c_float), ("bias_mode", C.c_int32), ("bias", C.c_void_p), ("bias_stride_z0", C.c_int64),
                 ("bias_stride_z1", C.c_int64), ("act", C.c_int32), ("accumulate", C.c_int32), ("preact", C.c_void_p),
                 ("split_k", C.c_int32), ("_pad2", C.c_int32), ("amax", C.c_void_p), ("drop_p", C.c_float),
-                ("_pad3", C.c_uint32), ("drop_seed", C.c_uint64), ("drop_seed_dev", C.c_void_p), ("addend", C.c_void_p)]
+                ("_pad3", C.c_uint32), ("drop_seed", C.c_uint64), ("drop_seed_dev", C.c_void_p), ("addend", C.c_void_p), ("colsum", C.c_void_p)]
 
 
 _P, _I, _L, _F, _U64, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_double
@@ -77,7 +77,7 @@ _PROTOS = {
     "sx_groupnorm_bwd": [_P, _P, _I, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "sx_seg_loss_fwd": [_P, _P, _I, _I, _L, _P, _P, _F, _P, _P, _P, _P],
     "sx_seg_loss_bwd": [_P, _P, _I, _I, _L, _P, _P, _F, _P, _P, _P],
-    "sx_adam_step": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _D, _D, _D, _F, _F, _F, _L, _I, _P, _P, _P, _P, _P, _P],
+    "sx_adam_step": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _D, _D, _D, _F, _F, _F, _L, _I, _P, _P, _P, _P, _P, _P],
     "sx_sgemm_small": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _L, _L, _L, _F, _I, _P],
 }
 # every symbol include/segtran_b200.h declares (checked by tests/test_abi.py)

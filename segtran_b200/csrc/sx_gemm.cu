@@ -54,6 +54,7 @@ struct GemmParams {
   unsigned long long drop_seed;
   const unsigned long long* drop_seed_dev;
   const float* addend;   // optional fp32 tensor in C's layout added to alpha*acc before bias/activation (tf32x3 passes)
+  float* colsum;         // optional [N]: += column sums of the stored values over all rows and batch slices (bias gradients)
   // descriptor fields (bring-up knobs; defaults are the canonical encodings)
   unsigned int lbo_k, sbo_k, lbo_mn_a, lbo_mn_b, sbo_mn, desc_version;
   int dbg_epi;      // bring-up: 0 normal, 1 skip global stores, 2 skip TMEM loads too
@@ -473,6 +474,34 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = sx::round_tf32(f[i]);
         }
+        if (p.colsum) {
+          // this thread's 8 columns (j, e), summed over its 4 rows, then over the 8 lanes that share the columns
+          float cs[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              float a = 0.f;
+#pragma unroll
+              for (int P = 0; P < 2; ++P)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                  if (row0 + 16 * P + 8 * h + tr < p.M) a += f[16 * P + 4 * j + 2 * h + e];
+              a += __shfl_xor_sync(0xffffffffu, a, 4);
+              a += __shfl_xor_sync(0xffffffffu, a, 8);
+              a += __shfl_xor_sync(0xffffffffu, a, 16);
+              cs[2 * j + e] = a;
+            }
+          if (tr == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int col = col0 + 8 * j + tc + e;
+                if (col < p.N) atomicAdd(p.colsum + col, cs[2 * j + e]);
+              }
+          }
+        }
         if (p.amax) {
 #pragma unroll
           for (int P = 0; P < 2; ++P)
@@ -724,6 +753,7 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
   p.bias_sz0 = a->bias_stride_z0; p.bias_sz1 = a->bias_stride_z1;
   p.act = a->act; p.accumulate = a->accumulate; p.preact = a->preact; p.amax = a->amax;
   p.addend = a->addend;
+  p.colsum = a->colsum;
   SX_REQUIRE(a->act != SX_ACT_GELU_BWD || (a->preact && a->c_dtype == SX_F32 && p.split_k == 1 && !a->accumulate),
              "sx_gemm: SX_ACT_GELU_BWD needs the fp32 pre-activation in `preact`, fp32 C, split_k=1, accumulate=0");
   SX_REQUIRE(!a->addend || (p.split_k == 1 && !a->accumulate && a->c_dtype == SX_F32), "sx_gemm: addend needs split_k=1, accumulate=0, fp32 C");

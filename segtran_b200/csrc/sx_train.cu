@@ -201,7 +201,8 @@ __global__ void adam_finalize_kernel(const double* __restrict__ sumsq, int P, fl
 }
 
 __global__ void __launch_bounds__(256)
-adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+adam_update_kernel(float* __restrict__ p, float* __restrict__ p_tf32, const float* __restrict__ g, float* __restrict__ m,
+                   float* __restrict__ v,
                    const int* __restrict__ seg_param, const long long* __restrict__ seg_off,
                    const int* __restrict__ seg_len, const float* __restrict__ coef, const float* __restrict__ lr_eff,
                    const float* __restrict__ wd, float b1, float omb1, float b2, float omb2, float eps) {
@@ -221,7 +222,9 @@ adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
     if (decay > 0.f) upd += decay * pp;
     m[off + i] = mm;
     v[off + i] = vv;
-    p[off + i] = pp - lr * upd;
+    const float pn = pp - lr * upd;
+    p[off + i] = pn;
+    if (p_tf32) p_tf32[off + i] = sx::round_tf32(pn);       // TF32 twin the next forward feeds to the tensor cores
   }
 }
 
@@ -260,7 +263,7 @@ extern "C" int sx_seg_loss_bwd(const float* logits, const float* mask, int32_t B
   return 0;
 }
 
-extern "C" int sx_adam_step(float* p, const float* g, float* m, float* v, const int32_t* seg_param,
+extern "C" int sx_adam_step(float* p, float* p_tf32, const float* g, float* m, float* v, const int32_t* seg_param,
                             const int64_t* seg_off, const int32_t* seg_len, int32_t nseg, int32_t P, const float* lr,
                             const float* wd, double b1, double b2, double eps, float grad_clip, float max_grad_norm,
                             float warmup, int64_t t_total, int32_t schedule, int64_t* step, double* sumsq, float* coef,
@@ -277,7 +280,7 @@ extern "C" int sx_adam_step(float* p, const float* g, float* m, float* v, const 
   adam_finalize_kernel<<<1, 256, 0, ST(stream)>>>(sumsq, P, grad_clip, max_grad_norm, lr, warmup, t_total, schedule,
                                                  reinterpret_cast<long long*>(step), coef, lr_eff, total_norm);
   SX_CHECK_CUDA(cudaGetLastError());
-  adam_update_kernel<<<nseg, 256, 0, ST(stream)>>>(p, g, m, v, seg_param, reinterpret_cast<const long long*>(seg_off),
+  adam_update_kernel<<<nseg, 256, 0, ST(stream)>>>(p, p_tf32, g, m, v, seg_param, reinterpret_cast<const long long*>(seg_off),
                                                    seg_len, coef, lr_eff, wd, (float)b1, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2),
                                                    (float)eps);
   SX_CHECK_CUDA(cudaGetLastError());

@@ -226,7 +226,7 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
                preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
                amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
                reduce_z1: bool = False, addend: Optional[torch.Tensor] = None,
-               gelu_bwd: Optional[torch.Tensor] = None) -> torch.Tensor:
+               gelu_bwd: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a [..., M, K], b [..., N, K] (strided fp32 views; either dim may be the contiguous one) ->
     out [z1, z0, M, N] fp32.  With reduce_z1 the z1 batch dim is summed into one output (atomic accumulate)."""
     _req_cuda(a, b, out, bias, preact, amax)
@@ -289,6 +289,10 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
         g.amax = amax.data_ptr()
     g.drop_p = drop_p
     g.drop_seed, g.drop_seed_dev = _seed_args(seed)
+    if colsum is not None:
+        if colsum.dtype != torch.float32 or colsum.numel() != N or not colsum.is_contiguous():
+            raise L.SxError("gemm_nt: colsum must be a contiguous fp32 [N] tensor")
+        g.colsum = colsum.data_ptr()
     if addend is not None:
         if addend.dtype != torch.float32 or tuple(addend.shape[-2:]) != (M, N) or _as4(addend).stride() != o4.stride():
             raise L.SxError("gemm_nt: addend must be an fp32 tensor in the output's layout")
@@ -315,13 +319,13 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = N
             preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
             amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
             reduce_z1: bool = False, gelu_bwd: Optional[torch.Tensor] = None,
-            addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+            addend: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C[..., m, n] = epilogue(alpha * sum_k a[..., m, k] b[..., n, k]) on the tcgen05 GEMM.  In the default
     precision this is one launch; in 'tf32x3' it is three passes on the hi/lo operand splits."""
     if _PRECISION == "tf32":
         return _gemm_nt_1(a, b, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
                           accumulate=accumulate, split_k=split_k, amax=amax, drop_p=drop_p, seed=seed,
-                          round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd, addend=addend)
+                          round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd, addend=addend, colsum=colsum)
     _req_cuda(a, b)
     ah, al = _tf32_split(a)
     bh, bl = _tf32_split(b)
@@ -340,7 +344,8 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = N
     _gemm_nt_1(al, bh, out=part, alpha=alpha, split_k=1, round_out=False, addend=addend)
     _gemm_nt_1(ah, bl, out=part, alpha=alpha, split_k=1, round_out=False, addend=part)
     return _gemm_nt_1(ah, bh, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
-                      split_k=1, amax=amax, drop_p=drop_p, seed=seed, round_out=False, addend=part, gelu_bwd=gelu_bwd)
+                      split_k=1, amax=amax, drop_p=drop_p, seed=seed, round_out=False, addend=part, gelu_bwd=gelu_bwd,
+                      colsum=colsum)
 
 
 def _pad4(n: int) -> int:
@@ -377,6 +382,12 @@ def _rowpad(t: torch.Tensor) -> torch.Tensor:
 def round_tf32(x: torch.Tensor) -> torch.Tensor:
     """fp32 -> fp32 rounded to the nearest TF32 value (weights, once per step)."""
     _req_cuda(x)
+    if _PRECISION == "tf32":
+        # parameters managed by train.FlatBertAdam carry a TF32-rounded twin that the optimiser kernel keeps current
+        # (`_sx_tf32`); it is valid as long as nobody modified the parameter in place since (version counter)
+        r = getattr(x, "_sx_tf32", None)
+        if r is not None and getattr(x, "_sx_tf32_version", -1) == x._version:
+            return r
     x = x.contiguous()
     if _PRECISION != "tf32":
         return x
@@ -737,7 +748,7 @@ class _AttnPVGeluGroupLinear(torch.autograd.Function):
         G = torch.empty((B, M, U1, Fd), device=P.device, dtype=torch.float32)
         H = torch.empty_like(G)
         gemm_nt(P, vv, out=G, bias=bm, gelu=True, preact=H, drop_p=drop_p, seed=seed)
-        Wr = round_tf32(Wo.reshape(M, Fd, Fd))
+        Wr = round_tf32(Wo).reshape(M, Fd, Fd)
         Y = torch.empty_like(G)
         gemm_nt(G, Wr.unsqueeze(0), out=Y, bias=bo.reshape(1, M, Fd), round_out=False)
         ctx.save_for_backward(P, v, H, G, Wr)
@@ -756,7 +767,13 @@ class _AttnPVGeluGroupLinear(torch.autograd.Function):
         dP = dv = dbm = dW = dbo = None
         # dH = mask * (dY Wo) * gelu'(H), TF32-rounded for the two GEMMs that consume it
         dH = torch.empty_like(H)
-        gemm_nt(dY, Wr.transpose(-1, -2).unsqueeze(0), out=dH, gelu_bwd=H, drop_p=drop_p, seed=ctx.seed)
+        # ... and the column sums of dH (= the gradient of MMSharedMid's bias) are accumulated by the same epilogue
+        dbm_buf = None
+        if has_bm and ctx.needs_input_grad[3]:
+            tgt = _grad_target(bm)
+            dbm_buf = tgt if tgt is not None else _zeros((Fd,), dY.device)
+            dbm = None if tgt is not None else dbm_buf
+        gemm_nt(dY, Wr.transpose(-1, -2).unsqueeze(0), out=dH, gelu_bwd=H, drop_p=drop_p, seed=ctx.seed, colsum=dbm_buf)
         if ctx.needs_input_grad[6]:
             tgt = _grad_target(Wo)
             if tgt is not None:
@@ -776,12 +793,6 @@ class _AttnPVGeluGroupLinear(torch.autograd.Function):
             dv = torch.empty_like(v)
             gemm_nt(P.transpose(-1, -2), dH.transpose(-1, -2), out=dv.view(B, U2, M, Fd).permute(0, 2, 1, 3),
                     round_out=False)
-        if has_bm and ctx.needs_input_grad[3]:
-            tgt = _grad_target(bm)
-            if tgt is not None:
-                colsum(dH.view(-1, Fd), out=tgt)
-            else:
-                dbm = colsum(dH.view(-1, Fd))
         return dP, dv, None, dbm, None, None, dW, dbo
 
 
@@ -825,7 +836,7 @@ class _GroupLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, G, Wo, bo):
         B, M, N, Fd = G.shape
-        Wr = round_tf32(Wo.reshape(M, Fd, Fd))
+        Wr = round_tf32(Wo).reshape(M, Fd, Fd)
         Y = torch.empty_like(G)
         gemm_nt(G, Wr.unsqueeze(0), out=Y, bias=bo.reshape(1, M, Fd), round_out=False)
         ctx.save_for_backward(G, Wr)
@@ -1230,7 +1241,7 @@ class _Conv1x1Add(torch.autograd.Function):
         B, Cin, V = x.shape
         Cout = W.shape[0]
         xr = round_tf32(x)                                   # the level below comes from outside (backbone): round once
-        Wr = round_tf32(W.reshape(Cout, Cin))
+        Wr = round_tf32(W).reshape(Cout, Cin)
         y = torch.empty((B, 1, Cout, V), device=x.device, dtype=torch.float32)
         ad = None if addend is None else addend.contiguous().view(B, 1, Cout, V)
         gemm_nt(Wr.view(1, 1, Cout, Cin), xr.view(B, 1, Cin, V).transpose(-1, -2), out=y, bias=b, bias_mode=L.SX_BIAS_M,

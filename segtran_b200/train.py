@@ -119,6 +119,12 @@ class FlatBertAdam:
                 seg_param.append(i)
                 seg_off.append(off + s)
                 seg_len.append(min(_SEG, n - s))
+        # TF32-rounded twin of the parameters, kept current by the update kernel: ops.round_tf32(p) returns the view in
+        # `p._sx_tf32` while p._version is unchanged, which removes the per-weight rounding pass from every forward.
+        # (In-place edits through torch bump the version and fall back to rounding on the fly; after raw `.data` edits
+        # call refresh_rounded().)
+        self.flat_r = torch.empty_like(self.flat_p)
+        self.refresh_rounded()
         self.flat_m = torch.zeros_like(self.flat_p)
         self.flat_v = torch.zeros_like(self.flat_p)
         P = len(self.params)
@@ -135,6 +141,13 @@ class FlatBertAdam:
         self.hyper = dict(b1=b1, b2=b2, e=e, max_grad_norm=max_grad_norm, grad_clip=grad_clip, warmup=warmup,
                           t_total=t_total, schedule=schedule)
 
+    def refresh_rounded(self):
+        L.call("sx_convert", self.flat_p.data_ptr(), L.SX_F32, self.flat_p.numel(), self.flat_r.data_ptr(), L.SX_F32, 1,
+               ops._stream())
+        for p, off in zip(self.params, self.bucket.offsets):
+            p._sx_tf32 = self.flat_r[off:off + p.numel()].view_as(p)
+            p._sx_tf32_version = p._version
+
     def zero_grad(self, set_to_none: bool = False):
         """One memset of the bucket (the .grad views stay attached; set_to_none is ignored on purpose)."""
         self.bucket.zero()
@@ -142,7 +155,7 @@ class FlatBertAdam:
     def step(self):
         h = self.hyper
         sched = L.SX_SCHED_WARMUP_LINEAR if h["schedule"] == "warmup_linear" else L.SX_SCHED_WARMUP_CONSTANT
-        L.call("sx_adam_step", self.flat_p.data_ptr(), self.bucket.flat.data_ptr(), self.flat_m.data_ptr(),
+        L.call("sx_adam_step", self.flat_p.data_ptr(), self.flat_r.data_ptr(), self.bucket.flat.data_ptr(), self.flat_m.data_ptr(),
                self.flat_v.data_ptr(), self._seg_param.data_ptr(), self._seg_off.data_ptr(), self._seg_len.data_ptr(),
                self._seg_param.numel(), len(self.params), self._lr.data_ptr(), self._wd.data_ptr(), h["b1"], h["b2"],
                h["e"], float(h["grad_clip"]), float(h["max_grad_norm"]), float(h["warmup"]), int(h["t_total"]), sched,

@@ -107,6 +107,10 @@ def test_gemm_gelu_bwd_epilogue_equals_separate_pass():
     close(fused.double(), sep.double(), 1e-6)
     frac = float((fused == 0).float().mean())
     assert abs(frac - 0.3) < 0.01
+    # column sums of the stored values (bias gradient) accumulated by the same epilogue, on top of what is already there
+    cs = torch.ones(136, device="cuda")
+    out = ops.gemm_nt(a, b, gelu_bwd=h, drop_p=0.3, seed=seed, round_out=False, colsum=cs)
+    close(cs.double(), 1.0 + out.double().sum(dim=(0, 1, 2)), 1e-5)
 
 
 def test_linear_fwd_bwd_gelu():
