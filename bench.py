@@ -7,12 +7,13 @@
 
 Workload (BASELINE.json configs[3], the config the metric is quoted on): Segtran3d BraTS 112^3 x 4ch,
 translayers=1, attractors=1024, modes=4, per-GPU batch 4, training mode (dropout 0.2, reference default
-train3d.py:213).  One step = forward + backward of the hot path
-    token flatten -> Squeeze-and-Expansion stack -> scatter -> voxel-wise head
+train3d.py:213).  One step = one training step of the hot path
+    token flatten -> Squeeze-and-Expansion stack -> scatter -> voxel-wise head -> BCE + Dice loss (train3d.py:731-756)
+    -> backward -> (N>1: one NCCL all-reduce of the flat gradient bucket) -> BertAdam update (optimization.py, --gradclip 0.1)
 on synthetic feature tensors of the shapes the I3D backbone / FPN pyramids produce at that config
-(feat_fpn [4,1024,14,14,14], curr_feat [4,832,56,56,56]) with a linear loss on the logits [4,4,112,112,112];
-gradients flow to both feature tensors and to every parameter; with N>1 the parameter gradients are averaged
-with one NCCL all-reduce (weak scaling: per-GPU batch fixed).  metric = voxels/s = N*4*112^3 / step time.
+(feat_fpn [4,1024,14,14,14], curr_feat [4,832,56,56,56]) and synthetic n-hot masks [4,4,112,112,112];
+gradients flow to both feature tensors and to every parameter (weak scaling: per-GPU batch fixed).
+metric = voxels/s = N*4*112^3 / step time.  `--impl reference` times the CPU oracle of the same step.
 """
 from __future__ import annotations
 
@@ -34,6 +35,8 @@ sys.path.insert(0, ROOT)
 CFG = dict(B=4, S=112, C0=1024, Cf=832, grid=(14, 14, 14), sp1=(56, 56, 56), classes=4, attractors=1024, modes=4,
            dropout=0.2)
 METRIC = "voxels/sec fwd+bwd Segtran3d BraTS 112^3 bs=4 hot path"
+WORKLOAD = ("Segtran3d BraTS 112^3x4ch translayers=1 attractors=1024 modes=4 bs=4/GPU hot path (flatten + squeeze-expansion "
+            "stack + voxel-wise head), fwd + BCE/Dice loss + bwd + BertAdam step, dropout 0.2")
 # training-step settings of the reference for --net segtran on BraTS (train3d.py:211-212, :223, :61, :73)
 TRAIN = dict(lr=2e-4, decay=1e-4, grad_clip=0.1, dice_w=0.5, bce_weight=[0., 3., 1., 1.75], warmup=0.05, t_total=10000)
 
@@ -187,8 +190,7 @@ def run_reference(args):
     line = {"metric": METRIC, "value": v, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "Segtran3d BraTS 112^3x4ch translayers=1 attractors=1024 bs=4 hot path (flatten+"
-                                   "squeeze-expansion stack+head), fwd + BCE/Dice loss + bwd + BertAdam step", "reference_sample": desc},
+            "config": {"workload": WORKLOAD, "reference_sample": desc},
             "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -486,8 +488,7 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-                "config": {"workload": "Segtran3d BraTS 112^3x4ch translayers=1 attractors=1024 modes=4 bs=4/GPU hot "
-                                       "path (flatten+squeeze-expansion stack+collapsed head), fwd+bwd, dropout 0.2",
+                "config": {"workload": WORKLOAD,
                            "global_batch": world * B, "tokens_per_sample": 2744, "parallelism": "dp%d" % world,
                            "l2": "inputs (2.4 GB/step) exceed the 126 MB L2; no explicit flush",
                            "grad_bucket_bytes": bucket.bytes(),
