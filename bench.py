@@ -473,6 +473,13 @@ def run_b200(args):
                 if isinstance(v, dict):
                     v["ms"] /= args.steps
             roof["per_launch"] = pl
+            roof["algorithmic_bytes_per_launch"] = sum(timer.gemm_bytes) / max(len(timer.gemm_bytes), 1)
+            try:        # DRAM bytes of the same 39 launches from an ncu capture of this command (profiles/, per launch)
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")))
+                roof["traffic"] = tr["dram_bytes_per_launch"]
+                roof["traffic_source"] = "profiles/r1_gemm_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+            except Exception:
+                pass
         else:
             src = "measured" if "hbm_gbs" in peaks else "fallback"
             peak = peaks.get("hbm_gbs", 6650.0)
