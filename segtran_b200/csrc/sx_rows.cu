@@ -584,6 +584,47 @@ __global__ void colsum_batched_kernel(const float* __restrict__ X, int Z1, long 
   }
 }
 
+// float4 flavour of both column sums: lane = 4 consecutive columns (512 B per warp and row), 4 rows in flight per thread.
+// out[z0*C + c] += sum_{z1,r} X[z1*sz1 + z0*sz0 + r*ld + c];  blockDim (32, 8), grid (C/128, row blocks, Z0)
+__global__ void __launch_bounds__(256)
+colsum_v4_kernel(const float* __restrict__ X, int Z1, long long sz1, long long sz0, long long R, int C, long long ld,
+                 float* __restrict__ out) {
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int z0 = blockIdx.z;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    const long long step = (long long)gridDim.y * blockDim.y;
+    for (int z1 = 0; z1 < Z1; ++z1) {
+      const float* base = X + z1 * sz1 + z0 * sz0 + c;
+      long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+      for (; r + 3 * step < R; r += 4 * step) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(base + r * ld));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(base + (r + step) * ld));
+        const float4 a2 = __ldg(reinterpret_cast<const float4*>(base + (r + 2 * step) * ld));
+        const float4 a3 = __ldg(reinterpret_cast<const float4*>(base + (r + 3 * step) * ld));
+        acc.x += (a0.x + a1.x) + (a2.x + a3.x); acc.y += (a0.y + a1.y) + (a2.y + a3.y);
+        acc.z += (a0.z + a1.z) + (a2.z + a3.z); acc.w += (a0.w + a1.w) + (a2.w + a3.w);
+      }
+      for (; r < R; r += step) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(base + r * ld));
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      }
+    }
+  }
+  __shared__ float4 s4[8][32];
+  s4[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = 0; y < 8; ++y) {
+      const float4 u = s4[y][threadIdx.x];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    float* o = out + (long long)z0 * C + c;
+    atomicAdd(o, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
+  }
+}
+
 // batched 2-D transpose: in [Z, R, C] -> out [Z, C, R]   (flatten / scatter, segtran3d.py:328-330, :478-480)
 __global__ void transpose_kernel(const float* __restrict__ in, int R, int C, float* __restrict__ out) {
   __shared__ float tile[32][33];
@@ -1025,7 +1066,13 @@ extern "C" int sx_colsum(const void* X, int32_t x_dtype, int64_t R, int32_t C, i
   if (gy > 64) gy = 64;
   if (gy < 1) gy = 1;
   dim3 grid(sx_ceil_div(C, 32), gy), blk(32, 8);
-  if (x_dtype == SX_F32)
+  if (x_dtype == SX_F32 && C % 4 == 0 && ld % 4 == 0 && al16(X)) {
+    int gy4 = (int)((R + 127) / 128);
+    const int cap = sx_ceil_div(sms_cached() * 8, sx_ceil_div(C, 128));
+    if (gy4 > cap) gy4 = cap;
+    if (gy4 < 1) gy4 = 1;
+    colsum_v4_kernel<<<dim3(sx_ceil_div(C, 128), gy4, 1), blk, 0, ST(stream)>>>((const float*)X, 1, 0, 0, R, C, ld, out);
+  } else if (x_dtype == SX_F32)
     colsum_kernel<float><<<grid, blk, 0, ST(stream)>>>((const float*)X, R, C, ld, out);
   else
     colsum_kernel<__nv_bfloat16><<<grid, blk, 0, ST(stream)>>>((const __nv_bfloat16*)X, R, C, ld, out);
@@ -1076,7 +1123,14 @@ extern "C" int sx_colsum_batched(const float* X, int32_t Z1, int64_t stride_z1, 
   if (gy > 32) gy = 32;
   if (gy < 1) gy = 1;
   dim3 grid(sx_ceil_div(C, 32), gy, Z0), blk(32, 8);
-  colsum_batched_kernel<<<grid, blk, 0, ST(stream)>>>(X, Z1, stride_z1, stride_z0, R, C, ld, out);
+  if (C % 4 == 0 && ld % 4 == 0 && stride_z0 % 4 == 0 && stride_z1 % 4 == 0 && al16(X)) {
+    int gy4 = (int)((R + 127) / 128);
+    const int cap = sx_ceil_div(sms_cached() * 8, sx_ceil_div(C, 128) * Z0);
+    if (gy4 > cap) gy4 = cap;
+    if (gy4 < 1) gy4 = 1;
+    colsum_v4_kernel<<<dim3(sx_ceil_div(C, 128), gy4, Z0), blk, 0, ST(stream)>>>(X, Z1, stride_z1, stride_z0, R, C, ld, out);
+  } else
+    colsum_batched_kernel<<<grid, blk, 0, ST(stream)>>>(X, Z1, stride_z1, stride_z0, R, C, ld, out);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
