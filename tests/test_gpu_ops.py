@@ -72,6 +72,40 @@ def test_gemm_nt_tf32x3_recovers_fp32_products():
     assert e1 > 1e-5          # the single-pass mode on un-rounded operands is visibly TF32
 
 
+def test_gemm_kernel_variants_agree():
+    """The CTA-pair kernel (tcgen05 cta_group::2, TMA-store / TMA reduce-add epilogue) and the 1-CTA kernel (register
+    stores / atomics) are two implementations of the same contract: same results on ragged, batched, MN-major, fused-epilogue
+    and split-K / batch-reduced problems."""
+    import segtran_b200._lib as L
+    from segtran_b200 import ops
+    a = tf32(torch.randn(2, 3, 300, 200, device="cuda"))
+    b = tf32(torch.randn(2, 3, 520, 200, device="cuda"))
+    am = a.transpose(-1, -2).contiguous().transpose(-1, -2)
+    bias = torch.randn(520, device="cuda")
+
+    def run():
+        h = torch.empty(2, 3, 300, 520, device="cuda")
+        y = ops.gemm_nt(a, b, bias=bias, gelu=True, preact=h, drop_p=0.25, seed=99)
+        red = ops.gemm_nt(am, b, reduce_z1=True, round_out=False)
+        sk = ops.gemm_nt(am, b[:1, :1], split_k=3, accumulate=True, out=torch.ones(2, 3, 300, 520, device="cuda"),
+                         round_out=False)
+        return y, h, red, sk
+
+    try:
+        L.call("sx_gemm_debug_set", b"cg2", 0)
+        ref = run()
+        for cg2, c_tma in ((1, 1), (1, 0)):
+            L.call("sx_gemm_debug_set", b"cg2", cg2)
+            L.call("sx_gemm_debug_set", b"c_tma", c_tma)
+            got = run()
+            assert torch.equal(got[0] == 0, ref[0] == 0)                  # identical dropout masks
+            for g, r in zip(got, ref):
+                close(g.double(), r.double(), 2e-6)
+    finally:
+        L.call("sx_gemm_debug_set", b"cg2", -1)
+        L.call("sx_gemm_debug_set", b"c_tma", -1)
+
+
 def test_epilogue_gelu_matches_fp64_erf():
     """The branch-free erf of the GEMM epilogue (sx_common.cuh erf_fast): |gelu - fp64 gelu| <= 4e-7 * max(1, |x|) over
     [-8, 8] — three orders below the TF32 operand rounding.  x is fed through an exact identity GEMM (TF32-exact inputs)."""
