@@ -131,3 +131,36 @@ def test_seg3d_shell_state_dict_matches_live_reference():
     assert sorted(a.keys()) == sorted(b.keys()) and len(bb_keys) > 0
     diff = [k for k in a if not torch.equal(a[k], b[k])]
     assert not diff, diff[:5]
+
+
+def test_zero_arena_hands_out_disjoint_aligned_slices_and_falls_back():
+    """ops._zeros: first step (no arena yet) falls back to torch.zeros and records the demand; from the second step on
+    every request is a zero-filled, 256-byte-aligned, non-overlapping slice of one arena; oversize requests fall back."""
+    import torch
+    from segtran_b200 import ops
+    dev = torch.device("cpu")
+    ops._zero_arena.pop((dev.type, dev.index), None)
+    a = ops._zeros((3, 5), dev)
+    b = ops._zeros((100,), dev)
+    assert ops._arena_state(dev)["buf"] is None and float(a.abs().sum() + b.abs().sum()) == 0.0
+    ops._begin_zero_arena(dev)
+    st = ops._arena_state(dev)
+    assert st["buf"] is not None and st["buf"].numel() == 64 + 128
+    a = ops._zeros((3, 5), dev)
+    b = ops._zeros((100,), dev)
+    base = st["buf"].data_ptr()
+    assert a.data_ptr() == base and b.data_ptr() == base + 64 * 4 and a.shape == (3, 5)
+    a.fill_(1.0)
+    assert float(b.abs().sum()) == 0.0                       # disjoint
+    c = ops._zeros((1000,), dev)                             # does not fit: plain allocation, still zero
+    assert c.data_ptr() < base or c.data_ptr() >= base + st["buf"].numel() * 4
+    ops._begin_zero_arena(dev)                               # next step: the arena grew to the demand just seen
+    assert ops._arena_state(dev)["buf"].numel() >= 64 + 128 + 1024
+    ops._zero_arena.pop((dev.type, dev.index), None)
+
+
+def test_split_k_model_prefers_full_waves():
+    from segtran_b200 import ops
+    assert ops._pick_split_k(2744, 1024, 1024, 16) == 1      # 1408 tiles: plenty of parallelism already
+    assert ops._pick_split_k(1024, 1024, 43904, 1) > 1       # 32 tiles, very long K: split
+    assert ops._pick_split_k(4, 832, 175616, 4) >= 4         # the head's weight gradient: a pure stream over K
