@@ -198,7 +198,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, dt, cores, desc = time_oracle(args.steps, args.warmup, float(os.environ.get("SEGTRAN_REF_BUDGET_S", "300")))
+    v, dt, cores, desc = time_oracle(args.steps, args.warmup, float(os.environ.get("SEGTRAN_REF_BUDGET_S", "180")))
     line = {"metric": METRIC, "value": v, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
