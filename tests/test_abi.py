@@ -55,3 +55,19 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in re.sub(r'""".*?"""', "", txt, flags=re.S), os.path.join(dp, f)
+
+
+def test_ctypes_prototypes_match_the_header_arity():
+    """Every `int sx_*(...)` declaration of include/segtran_b200.h has a ctypes prototype with the same number of
+    parameters (a stale binding would shift every later argument)."""
+    import os
+    import re
+    from segtran_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "segtran_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    decls = dict((m.group(1), m.group(2)) for m in re.finditer(r"\bint\s+(sx_\w+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S))
+    assert set(_lib._PROTOS) <= set(decls), sorted(set(_lib._PROTOS) - set(decls))
+    for name, proto in _lib._PROTOS.items():
+        params = decls[name].strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(proto), "%s: header declares %d parameters, ctypes prototype has %d" % (name, n, len(proto))
