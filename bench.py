@@ -300,11 +300,12 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(1337 + rank)
+    torch.manual_seed(1337)                      # the same initial weights on every rank (data parallelism) ...
     cfg = S3.Segtran3dConfig()
     with contextlib.redirect_stdout(open(os.devnull, "w")):
         cfg.update_config(model_args("cuda", CFG["dropout"]))
         net = S3.Segtran3d(cfg, backbone=torch.nn.Identity()).to(dev).train()
+    torch.manual_seed(1337 + rank)               # ... different synthetic data and dropout masks per rank
     hot_params = list(net.voxel_fusion.parameters()) + list(net.out_fpn_bridgeconv3d.parameters()) + \
         list(net.out_conv3d.parameters())
     use_graph = not args.no_graph
