@@ -142,6 +142,7 @@ def _req_cuda(*ts):
 # the first step) requests fall back to torch.zeros.
 # ------------------------------------------------------------------------------------------------
 _zero_arena = {}
+_ARENA_MAX = 1 << 26          # floats (256 MB)
 
 
 def _arena_state(device):
@@ -163,7 +164,9 @@ def _zeros(shape, device) -> torch.Tensor:
         n *= int(d)
     st = _arena_state(device)
     off, n_al = st["off"], (n + 63) // 64 * 64           # 256-byte slots (TMA / vector accesses stay legal)
-    st["off"] = off + n_al
+    # the running demand sizes the next arena; it is capped so that many forwards without a step boundary in between
+    # (evaluation loops) cannot inflate it
+    st["off"] = min(off + n_al, _ARENA_MAX)
     if st["buf"] is not None and off + n_al <= st["buf"].numel():
         return st["buf"][off:off + n].view(tuple(shape))
     return torch.zeros(tuple(shape), device=device, dtype=torch.float32)
