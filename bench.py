@@ -289,7 +289,6 @@ class KernelTimer:
 def run_b200(args):
     import torch.distributed as dist
     from segtran_b200 import _lib as L
-    from segtran_b200 import ops
     from segtran_b200.networks import segtran3d as S3
     from segtran_b200.parallel import GradBucket
 

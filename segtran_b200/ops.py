@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Optional, Sequence
+from typing import Optional
 
 import torch
 

@@ -9,7 +9,7 @@ counter live on the GPU, so forward + loss + backward + update can sit in one CU
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional
+from typing import List, Optional
 
 import torch
 
