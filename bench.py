@@ -88,7 +88,7 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle (CPU restatement of the reference) timed on the host cores
 # ----------------------------------------------------------------------------------------------------------
-def oracle_step_factory(sample_B=1, crop=1):
+def oracle_step_factory(sample_B=1, crop=1, device="cpu"):
     """One fwd+bwd of the reference formulation on CPU for `sample_B` samples (optionally a spatial crop)."""
     from oracle import segtran_oracle as O
     torch.manual_seed(1337)
@@ -99,37 +99,38 @@ def oracle_step_factory(sample_B=1, crop=1):
     p = {}
 
     def lin(name, o, i, bias=True, std=0.02):
-        p[name + ".weight"] = (torch.randn(o, i) * std).requires_grad_()
+        p[name + ".weight"] = torch.randn(o, i) * std
         if bias:
-            p[name + ".bias"] = torch.zeros(o).requires_grad_()
+            p[name + ".bias"] = torch.zeros(o)
 
     vf = "voxel_fusion."
     lin(vf + "pos_code_layer.pos_coder.pos_fc", C0, 3)
-    p[vf + "vfeat_norm_layers.0.weight"] = torch.ones(C0).requires_grad_()
-    p[vf + "vfeat_norm_layers.0.bias"] = torch.zeros(C0).requires_grad_()
+    p[vf + "vfeat_norm_layers.0.weight"] = torch.ones(C0)
+    p[vf + "vfeat_norm_layers.0.bias"] = torch.zeros(C0)
     t = vf + "translayers.0."
-    p[t + "attractors"] = torch.randn(1, A, C0).requires_grad_()
+    p[t + "attractors"] = torch.randn(1, A, C0)
     for pre, m, Fd in ((t + "in_ator_trans.", 1, C0), (t + "ator_out_trans.", M, C0)):
         lin(pre + "query", C0, C0)
         lin(pre + "out_trans.first_linear", m * Fd, C0, bias=False)
-        p[pre + "out_trans.first_norm_layer.weight"] = torch.ones(Fd).requires_grad_()
-        p[pre + "out_trans.first_norm_layer.bias"] = torch.zeros(Fd).requires_grad_()
+        p[pre + "out_trans.first_norm_layer.weight"] = torch.ones(Fd)
+        p[pre + "out_trans.first_norm_layer.bias"] = torch.zeros(Fd)
         lin(pre + "out_trans.feat_softaggr.feat2score", 1, Fd)
         lin(pre + "out_trans.intermediate.shared_linear", Fd, Fd)
-        p[pre + "out_trans.output.group_linear.weight"] = (torch.randn(m * Fd, Fd, 1) * 0.02).requires_grad_()
-        p[pre + "out_trans.output.group_linear.bias"] = torch.zeros(m * Fd).requires_grad_()
-        p[pre + "out_trans.output.resout_norm_layer.weight"] = torch.ones(Fd).requires_grad_()
-        p[pre + "out_trans.output.resout_norm_layer.bias"] = torch.zeros(Fd).requires_grad_()
-    p["out_fpn_bridgeconv3d.weight"] = (torch.randn(C0, Cf, 1, 1, 1) * 0.02).requires_grad_()
-    p["out_fpn_bridgeconv3d.bias"] = torch.zeros(C0).requires_grad_()
-    p["out_conv3d.weight"] = (torch.randn(K, C0, 1, 1, 1) * 0.02).requires_grad_()
-    p["out_conv3d.bias"] = torch.zeros(K).requires_grad_()
+        p[pre + "out_trans.output.group_linear.weight"] = (torch.randn(m * Fd, Fd, 1) * 0.02)
+        p[pre + "out_trans.output.group_linear.bias"] = torch.zeros(m * Fd)
+        p[pre + "out_trans.output.resout_norm_layer.weight"] = torch.ones(Fd)
+        p[pre + "out_trans.output.resout_norm_layer.bias"] = torch.zeros(Fd)
+    p["out_fpn_bridgeconv3d.weight"] = (torch.randn(C0, Cf, 1, 1, 1) * 0.02)
+    p["out_fpn_bridgeconv3d.bias"] = torch.zeros(C0)
+    p["out_conv3d.weight"] = (torch.randn(K, C0, 1, 1, 1) * 0.02)
+    p["out_conv3d.bias"] = torch.zeros(K)
+    p = {k: v.to(device).requires_grad_() for k, v in p.items()}
     from oracle import train_oracle as T
-    feat = torch.randn(sample_B, C0, *g, requires_grad=True)
-    curr = torch.randn(sample_B, Cf, *sp1, requires_grad=True)
-    Y = (torch.rand(sample_B, K, S, S, S) > 0.7).float()                   # synthetic n-hot masks
-    pw, cw = T.normalised_bce_weight(TRAIN["bce_weight"], K), T.default_class_weights(K)
-    vmask = torch.ones(sample_B, g[0] * g[1] * g[2])
+    feat = torch.randn(sample_B, C0, *g).to(device).requires_grad_()
+    curr = torch.randn(sample_B, Cf, *sp1).to(device).requires_grad_()
+    Y = (torch.rand(sample_B, K, S, S, S) > 0.7).float().to(device)        # synthetic n-hot masks
+    pw, cw = T.normalised_bce_weight(TRAIN["bce_weight"], K).to(device), T.default_class_weights(K).to(device)
+    vmask = torch.ones(sample_B, g[0] * g[1] * g[2], device=device)
     names = list(p.keys())
     params = [p[k] for k in names]
     leaves = params + [feat, curr]

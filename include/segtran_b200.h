@@ -94,6 +94,42 @@ typedef struct {
 
 int sx_gemm(const sx_gemm_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused attention probabilities of the squeeze-out stage (csrc/sx_attn.cu):
+ *     P[b][m] = dropout( softmax_keys( min(alpha * Q[b,:,m] K[b,:,m]^T, clip) ) )
+ * One persistent tcgen05 kernel replaces segtran_shared.py:566-567 (Q.K^T / sqrt(d)), :569-580 (max statistics and
+ * conditional clamp), :601 (softmax) and :605 (attention dropout): the scores stay in TMEM, the softmax runs on the
+ * tcgen05.ld fragments, only P is written (plus the raw scaled scores S when the backward needs them).
+ * Q [Bq][U1][M*d] (q_bstride = 0: one query bank shared by the batch), K [B][U2][M*d]; mode m uses columns
+ * [m*d, (m+1)*d).  P, S: [B][M][U1][ldp] fp32, ldp % 4 == 0.  lse, rowmax: [B][M][U1] (natural-log units; rowmax is
+ * the max of the raw row).  stat: device scratch of two 32-bit words, ZERO-initialised by the caller: [0] the running
+ * maximum of the scores under an order-preserving float->uint map (0 = none yet), [1] (float) number of rows whose
+ * maximum is below -(clip - 104).  diag (optional, device float[3]): [0] running
+ * max, [1] += 1 when the clamp fired (max > clip), [2] += stat[1] in that case (rows where the reference's LOWER
+ * clamp could have mattered — the upper clamp is applied exactly; see sx_attn.cu).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, M, U1, U2, d;
+  int32_t round_tf32;
+  const float* Q;
+  int64_t q_ld, q_bstride;
+  const float* K;
+  int64_t k_ld, k_bstride;
+  float alpha, clip;
+  float* P;
+  float* S;                      /* optional */
+  int64_t ldp;
+  float* lse;
+  float* rowmax;                 /* optional */
+  float* stat;
+  float* diag;                   /* optional */
+  float drop_p;
+  uint32_t _pad;
+  uint64_t drop_seed;
+  const uint64_t* drop_seed_dev;
+} sx_attn_probs_args;
+int sx_attn_probs_fwd(const sx_attn_probs_args* args, void* stream);
+
 /* Dropout seeds: every dropout-capable entry takes `seed` (by value) and `seed_dev` (device pointer or NULL); the
  * effective seed is seed + *seed_dev, read on the device in stream order, so a captured CUDA graph draws a new mask
  * on every replay.  sx_seed_derive writes out[0] = base[0] + add (the per-call seed an op keeps for its backward);

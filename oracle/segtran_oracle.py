@@ -239,11 +239,12 @@ def seg_head_2d(p: Params, curr_feat: Tensor, vfeat_fused: Tensor, grid: Sequenc
     return F.interpolate(s, size=tuple(out_size), mode="bilinear", align_corners=False)
 
 
-def voxels_pos_for_grid(grid: Sequence[int], scales: Sequence[float], B: int, dtype=torch.float32) -> Tensor:
+def voxels_pos_for_grid(grid: Sequence[int], scales: Sequence[float], B: int, dtype=torch.float32,
+                        device="cpu") -> Tensor:
     """Pixel coordinates of the token grid: gen_all_indices(grid) * per-axis model scale, repeated over
     the batch (segtran3d.py:442-470, segtran2d.py:364-382)."""
-    idx = gen_all_indices(tuple(grid)).reshape(-1, len(grid)).to(dtype)
-    idx = idx * torch.tensor([list(scales)], dtype=dtype)
+    idx = gen_all_indices(tuple(grid), device=device).reshape(-1, len(grid)).to(dtype)
+    idx = idx * torch.tensor([list(scales)], dtype=dtype, device=device)
     return idx.unsqueeze(0).repeat(B, 1, 1)
 
 
@@ -257,7 +258,7 @@ def hot_path_3d(p: Params, feat_fpn: Tensor, curr_feat: Tensor, vmask: Tensor, o
     grid = tuple(feat_fpn.shape[2:])
     H, W, D = out_size
     scales = (D // grid[0], H // grid[1], W // grid[2])                      # segtran3d.py:446-456
-    pos = voxels_pos_for_grid(grid, scales, B, feat_fpn.dtype)
+    pos = voxels_pos_for_grid(grid, scales, B, feat_fpn.dtype, feat_fpn.device)
     tok = flatten_tokens(feat_fpn)
     fused = fusion_encoder(p, "voxel_fusion.", tok, pos, vmask.reshape(B, -1, 1), translayer_dims,
                            num_modes, **kw)
@@ -270,7 +271,7 @@ def hot_path_2d(p: Params, feat_fpn: Tensor, curr_feat: Tensor, vmask: Tensor, o
     B = feat_fpn.shape[0]
     grid = tuple(feat_fpn.shape[2:])
     H, W = out_size
-    pos = voxels_pos_for_grid(grid, (H // grid[0], W // grid[1]), B, feat_fpn.dtype)
+    pos = voxels_pos_for_grid(grid, (H // grid[0], W // grid[1]), B, feat_fpn.dtype, feat_fpn.device)
     tok = flatten_tokens(feat_fpn)
     fused = fusion_encoder(p, "voxel_fusion.", tok, pos, vmask.reshape(B, -1, 1), translayer_dims,
                            num_modes, **kw)

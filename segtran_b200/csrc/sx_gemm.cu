@@ -18,15 +18,11 @@
 #include <string>
 
 #include "sx_common.cuh"
+#include "sx_tc.cuh"
 
 namespace {
+using namespace sxtc;
 
-constexpr int BM = 128;          // tile rows   (UMMA M)
-constexpr int BN = 256;          // tile cols   (UMMA N)
-constexpr int BKB = 128;         // bytes of K per stage row (one 128B swizzle span)
-constexpr int KSTEPS = 4;        // UMMA instructions per stage (each covers 32 bytes of K)
-constexpr int A_STAGE_BYTES = BM * BKB;       // 16 KB
-constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 384;         // warps 0-3: TMA / MMA / TMEM alloc / idle;  warps 4-11: epilogue (2 per lane quarter)
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int SMEM_BYTES = 192 * 1024 /*4 x 48 KB stages*/ + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -62,20 +58,6 @@ struct GemmParams {
   int c_tma;        // pair kernel: C (and preact) leave through shared memory + TMA bulk stores (full 128-byte lines);
                     // 2 = accumulate mode: TMA reduce-add (split-K / batch-reduced gradients) instead of atomics
 };
-
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t version, uint32_t layout_type) {
-  // cute::UMMA::SmemDescriptor: start[0,14) lbo[16,30) sbo[32,46) version[46,48) layout_type[61,64)
-  //   layout_type 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks; the only layout the
-  //   tensor core accepts for MN-major 32-bit (tf32) operands, cutlass sm100_common.inl:92)
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)(version & 0x3) << 46;
-  d |= (uint64_t)(layout_type & 0x7) << 61;
-  return d;
-}
 
 // CG2: CTA-pair mode (tcgen05 cta_group::2).  The two CTAs of a 2-cluster compute one 256 x 256 tile: each loads its own
 // 128 rows of A and HALF of the B tile (128 of the 256 columns), the leader (even) CTA issues 256-row UMMAs that read A
@@ -545,23 +527,6 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(f);
-  });
-  return fn;
-}
-
 struct DebugKnobs {
   long long lbo_k = 16, sbo_k = 1024, sbo_mn = -1, desc_version = 1;   // sbo_mn -1: canonical (1024 B; 512 B for tf32)
   long long lbo_mn_a = -1, lbo_mn_b = -1;     // -1: canonical (BK rows * 128 B)
@@ -573,78 +538,12 @@ struct DebugKnobs {
 };
 DebugKnobs g_knobs;
 
-int make_map(CUtensorMap* tm, const sx_operand& op, int es, int rows, int K, int Z0, int Z1, int box_rows,
-             const char* name) {
-  PFN_encodeTiled enc = get_encode();
-  SX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
-  SX_REQUIRE((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0, "sx_gemm: operand %s not 16-byte aligned", name);
-  SX_REQUIRE((op.ld * es) % 16 == 0, "sx_gemm: operand %s ld*elsize (%lld) not a multiple of 16", name,
-             (long long)op.ld * es);
-  const int z0 = op.stride_z0 ? Z0 : 1, z1 = op.stride_z1 ? Z1 : 1;
-  SX_REQUIRE((op.stride_z0 * es) % 16 == 0 && (op.stride_z1 * es) % 16 == 0,
-             "sx_gemm: operand %s batch strides not multiples of 16 bytes", name);
-  const int inner = BKB / es;      // elements in a 128-byte span
-  cuuint64_t gdim[4];
-  cuuint64_t gstr[3];
-  cuuint32_t box[4];
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  if (op.major == SX_MAJOR_K) {
-    gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)rows;
-    box[0] = inner; box[1] = box_rows;
-  } else {
-    gdim[0] = (cuuint64_t)rows; gdim[1] = (cuuint64_t)K;
-    box[0] = inner; box[1] = inner;            // BK rows of k, each 128 B of mn
-  }
-  gdim[2] = z0; gdim[3] = z1;
-  box[2] = 1; box[3] = 1;
-  gstr[0] = (cuuint64_t)op.ld * es;
-  const cuuint64_t dflt = gstr[0] * gdim[1];
-  gstr[1] = op.stride_z0 ? (cuuint64_t)op.stride_z0 * es : dflt;
-  gstr[2] = op.stride_z1 ? (cuuint64_t)op.stride_z1 * es : (gstr[1] * gdim[2]);
-  CUtensorMapDataType dt = (es == 4) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  // MN-major fp32 (tf32) operands use the 32-byte-atom flavour of the 128-byte swizzle (UMMA SWIZZLE_128B_BASE32B)
-  const CUtensorMapSwizzle sw = (es == 4 && op.major == SX_MAJOR_MN) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
-                                                                     : CU_TENSOR_MAP_SWIZZLE_128B;
-  CUresult r = enc(tm, dt, 4, const_cast<void*>(op.ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  SX_REQUIRE(r == CUDA_SUCCESS,
-             "cuTensorMapEncodeTiled(%s) failed: %d (gdim %llu,%llu,%llu,%llu gstr %llu,%llu,%llu box %u,%u)", name,
-             (int)r, (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
-             (unsigned long long)gdim[3], (unsigned long long)gstr[0], (unsigned long long)gstr[1],
-             (unsigned long long)gstr[2], box[0], box[1]);
-  return 0;
-}
-
-// fp32 output tensor [Z1][Z0][M][N] (row pitch ldc) as a 4-D tensor map with 32-column x 16-row boxes, 128-byte swizzle
-int make_out_map(CUtensorMap* tm, void* ptr, const sx_gemm_args* a) {
-  PFN_encodeTiled enc = get_encode();
-  SX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
-  const bool z1_reduced = a->Z1 > 1 && a->c_stride_z1 == 0;
-  cuuint64_t gdim[4] = {(cuuint64_t)a->N, (cuuint64_t)a->M, (cuuint64_t)a->Z0, (cuuint64_t)(z1_reduced ? 1 : a->Z1)};
-  cuuint64_t gstr[3];
-  gstr[0] = (cuuint64_t)a->ldc * 4;
-  gstr[1] = a->Z0 > 1 ? (cuuint64_t)a->c_stride_z0 * 4 : gstr[0] * gdim[1];
-  gstr[2] = (a->Z1 > 1 && !z1_reduced) ? (cuuint64_t)a->c_stride_z1 * 4 : gstr[1] * gdim[2];
-  cuuint32_t box[4] = {32, 16, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  SX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(C) failed: %d (N %d M %d ldc %lld)", (int)r, a->N, a->M,
-             (long long)a->ldc);
-  return 0;
-}
-
 template <int ES, bool A_MN, bool B_MN, bool CG2>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
            const GemmParams& p, int grid, cudaStream_t st) {
   auto kern = sx_gemm_kernel<ES, A_MN, B_MN, CG2>;
   constexpr int smem_bytes = CG2 ? SMEM_BYTES_CG2 : SMEM_BYTES;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  });
-  SX_CHECK_CUDA(attr_err);
+  SX_CHECK_CUDA(set_max_smem_once(kern, smem_bytes));         // per device (a process may drive several GPUs)
   if constexpr (CG2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -664,16 +563,6 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   }
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
-}
-
-int sm_count_cached() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
-  }
-  return n;
 }
 
 }  // namespace
@@ -785,10 +674,10 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
       (a->Z0 == 1 || (a->c_stride_z0 > 0 && a->c_stride_z0 % 4 == 0)) &&
       (a->Z1 == 1 || z1_reduced || (a->c_stride_z1 > 0 && a->c_stride_z1 % 4 == 0)) &&
       (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 && (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0)) {
-    rc = make_out_map(&tc, a->C, a);
+    rc = make_out_map(&tc, a->C, a->N, a->M, a->Z0, a->Z1, a->ldc, a->c_stride_z0, a->c_stride_z1);
     if (rc) return rc;
     if (a->preact && a->act != SX_ACT_GELU_BWD) {
-      rc = make_out_map(&tp, a->preact, a);
+      rc = make_out_map(&tp, a->preact, a->N, a->M, a->Z0, a->Z1, a->ldc, a->c_stride_z0, a->c_stride_z1);
       if (rc) return rc;
     }
     p.c_tma = a->accumulate ? 2 : 1;

@@ -510,6 +510,39 @@ class _AttnScores(torch.autograd.Function):
         return dq, dk, None, None, drb
 
 
+def attn_probs_fused(q, k, M, clip=500.0, drop_p=0.0, seed=0, diag=None, need_scores=False, round_out=True):
+    """P = dropout(softmax(min(Q K^T / sqrt(d), clip))) per mode in ONE tcgen05 kernel (csrc/sx_attn.cu): the scores stay
+    in TMEM and the softmax runs on the tcgen05.ld fragments (reference segtran_shared.py:566-567, :569-580, :601, :605).
+    q [Bq,U1,M*d] (Bq = 1 broadcasts), k [B,U2,M*d], both contiguous fp32 (TF32-rounded by their producers).
+    -> (P [B,M,U1,U2] view of a row-padded buffer, S or None (raw scaled scores, same layout), lse [B,M,U1],
+        rowmax [B,M,U1], stat [2])."""
+    _req_cuda(q, k)
+    if q.dtype != torch.float32 or k.dtype != torch.float32 or not q.is_contiguous() or not k.is_contiguous():
+        raise L.SxError("attn_probs_fused: contiguous fp32 q/k expected")
+    Bq, U1, Cq = q.shape
+    B, U2, Ck = k.shape
+    if Cq != Ck or Cq % M or (Cq // M) % 4 or Bq not in (1, B):
+        raise L.SxError("attn_probs_fused: bad shapes q %s k %s modes %d" % (tuple(q.shape), tuple(k.shape), M))
+    d = Cq // M
+    P = _rowpad_empty((B, M, U1, U2), q.device)
+    S = _rowpad_empty((B, M, U1, U2), q.device) if need_scores else None
+    lse = torch.empty((B, M, U1), device=q.device, dtype=torch.float32)
+    rowmax = torch.empty((B, M, U1), device=q.device, dtype=torch.float32)
+    stat = _zeros((2,), q.device)
+    a = L.sx_attn_probs_args()
+    a.B, a.M, a.U1, a.U2, a.d = B, M, U1, U2, d
+    a.round_tf32 = 1 if (round_out and _PRECISION == "tf32") else 0
+    a.Q, a.q_ld, a.q_bstride = q.data_ptr(), Cq, (0 if Bq == 1 else U1 * Cq)
+    a.K, a.k_ld, a.k_bstride = k.data_ptr(), Ck, U2 * Ck
+    a.alpha, a.clip = 1.0 / math.sqrt(d), float(clip)
+    a.P, a.S, a.ldp = P.data_ptr(), _ptr(S), P.stride(-2)
+    a.lse, a.rowmax, a.stat, a.diag = lse.data_ptr(), rowmax.data_ptr(), stat.data_ptr(), _ptr(diag)
+    a.drop_p = drop_p
+    a.drop_seed, a.drop_seed_dev = _seed_args(seed)
+    L.call("sx_attn_probs_fwd", C.byref(a), _stream())
+    return P, S, lse, rowmax, stat
+
+
 class _Scale(torch.autograd.Function):
     """y = alpha * x (sx_scale kernel)."""
 
