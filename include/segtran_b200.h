@@ -38,7 +38,12 @@ enum { SX_OP_TF32 = 0, SX_OP_BF16 = 1 };
 enum { SX_MAJOR_K = 0, SX_MAJOR_MN = 1 };
 enum { SX_BIAS_NONE = 0, SX_BIAS_N = 1, SX_BIAS_M = 2 };
 enum { SX_ACT_NONE = 0, SX_ACT_GELU = 1,
-       SX_ACT_GELU_BWD = 2 /* C = dropmask * (alpha A.B^T) * gelu'(preact): `preact` is an INPUT in C's layout */ };
+       SX_ACT_GELU_BWD = 2 /* C = dropmask * (alpha A.B^T) * gelu'(preact): `preact` is an INPUT in C's layout */,
+       SX_ACT_SOFTMAX_BWD = 3 /* C = dS = P * (dropmask * (alpha A.B^T) - row_dot[m]), zero where the score was clamped:
+                                 the softmax backward (segtran_shared.py:601-605) in the epilogue of the dP = dU V^T product.
+                                 P = exp(min(S, clip) - row_lse[m]) is recomputed from the raw scaled scores S given through
+                                 `preact` (C's layout); drop_* describe the ATTENTION dropout of the forward (index = flat
+                                 index in C's layout, the layout of P) */ };
 
 int sx_version(void);
 const char* sx_last_error(void);
@@ -90,6 +95,14 @@ typedef struct {
                                     error-compensated 3-pass TF32 mode (A_hi B_hi + A_lo B_hi + A_hi B_lo) */
   float* colsum;                 /* optional [N] fp32: += column sums of the stored values over all rows and batch slices
                                     (a bias gradient that would otherwise need its own pass over the output) */
+  float* rowdot;                 /* SX_ACT_GELU_BWD only, optional [Z1][Z0][M] fp32 (contiguous): += sum_n C[m][n] *
+                                    (preact[m][n] - rowdot_sub[n]) — with C = dU and preact - bias = U = P.V this is the
+                                    softmax backward's row term sum_a P_a dP_a = sum_f dU_f U_f, obtained without a pass over P */
+  const float* rowdot_sub;       /* [N] fp32 or NULL (= zeros) */
+  const float* row_lse;          /* SX_ACT_SOFTMAX_BWD: [Z1][Z0][M] log-sum-exp of the clamped score rows */
+  const float* row_dot;          /* SX_ACT_SOFTMAX_BWD: [Z1][Z0][M] the row term produced through `rowdot` */
+  float clip;                    /* SX_ACT_SOFTMAX_BWD: attention clamp (scores above it were clamped: zero gradient) */
+  int32_t _pad4;
 } sx_gemm_args;
 
 int sx_gemm(const sx_gemm_args* args, void* stream);

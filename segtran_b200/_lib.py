@@ -15,7 +15,7 @@ SX_F32, SX_BF16 = 0, 1
 SX_OP_TF32, SX_OP_BF16 = 0, 1
 SX_MAJOR_K, SX_MAJOR_MN = 0, 1
 SX_BIAS_NONE, SX_BIAS_N, SX_BIAS_M = 0, 1, 2
-SX_ACT_NONE, SX_ACT_GELU, SX_ACT_GELU_BWD = 0, 1, 2
+SX_ACT_NONE, SX_ACT_GELU, SX_ACT_GELU_BWD, SX_ACT_SOFTMAX_BWD = 0, 1, 2, 3
 SX_SCHED_WARMUP_LINEAR, SX_SCHED_WARMUP_CONSTANT = 0, 1
 
 
@@ -35,7 +35,9 @@ class sx_gemm_args(C.Structure):
                 ("alpha", C.c_float), ("bias_mode", C.c_int32), ("bias", C.c_void_p), ("bias_stride_z0", C.c_int64),
                 ("bias_stride_z1", C.c_int64), ("act", C.c_int32), ("accumulate", C.c_int32), ("preact", C.c_void_p),
                 ("split_k", C.c_int32), ("_pad2", C.c_int32), ("amax", C.c_void_p), ("drop_p", C.c_float),
-                ("_pad3", C.c_uint32), ("drop_seed", C.c_uint64), ("drop_seed_dev", C.c_void_p), ("addend", C.c_void_p), ("colsum", C.c_void_p)]
+                ("_pad3", C.c_uint32), ("drop_seed", C.c_uint64), ("drop_seed_dev", C.c_void_p), ("addend", C.c_void_p), ("colsum", C.c_void_p),
+                ("rowdot", C.c_void_p), ("rowdot_sub", C.c_void_p), ("row_lse", C.c_void_p), ("row_dot", C.c_void_p),
+                ("clip", C.c_float), ("_pad4", C.c_int32)]
 
 
 class sx_attn_probs_args(C.Structure):

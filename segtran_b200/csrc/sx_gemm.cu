@@ -51,6 +51,11 @@ struct GemmParams {
   const unsigned long long* drop_seed_dev;
   const float* addend;   // optional fp32 tensor in C's layout added to alpha*acc before bias/activation (tf32x3 passes)
   float* colsum;         // optional [N]: += column sums of the stored values over all rows and batch slices (bias gradients)
+  float* rowdot;         // GELU_BWD: optional [Z1][Z0][M]: += sum_n C[m][n] * (preact[m][n] - rowdot_sub[n])
+  const float* rowdot_sub;
+  const float* row_lse;  // SOFTMAX_BWD: [Z1][Z0][M]
+  const float* row_dot;  // SOFTMAX_BWD: [Z1][Z0][M]
+  float clip;
   // descriptor fields (bring-up knobs; defaults are the canonical encodings)
   unsigned int lbo_k, sbo_k, lbo_mn_a, lbo_mn_b, sbo_mn, desc_version;
   int dbg_epi;      // bring-up: 0 normal, 1 skip global stores, 2 skip TMEM loads too
@@ -362,6 +367,17 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      float rdot[4] = {0.f, 0.f, 0.f, 0.f};             // [P][h] GELU_BWD row dot products of this tile
+      float sm_lse[4] = {0.f, 0.f, 0.f, 0.f}, sm_dot[4] = {0.f, 0.f, 0.f, 0.f};
+      const long long zrow = ((long long)z1 * p.Z0 + z0) * p.M;
+      if (p.act == SX_ACT_SOFTMAX_BWD) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = row0 + 16 * (i >> 1) + 8 * (i & 1) + tr;
+          sm_lse[i] = r < p.M ? p.row_lse[zrow + r] * 1.4426950408889634f : 0.f;
+          sm_dot[i] = r < p.M ? p.row_dot[zrow + r] : 0.f;
+        }
+      }
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         const int col0 = nb * BN + c * 32;
@@ -398,11 +414,90 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
           }
         }
+        auto apply_dropout = [&]() {
+          if (p.drop_p > 0.f) {
+            const float keep_scale = 1.f / (1.f - p.drop_p);
+            const uint32_t p16 = sx::drop_p16(p.drop_p);
+            const unsigned long long dseed = p.drop_seed + (p.drop_seed_dev ? *p.drop_seed_dev : 0ull);
+            if (((p.ldc | zoff) & 3) == 0) {
+              // rows start on a 4-element hash group: this thread's pair is always elements (tc&2, tc&2 + 1) of its
+              // group, i.e. one 32-bit word per pair with a per-thread constant multiplier / key
+              const int w = (tc >> 1) & 1;
+              const uint32_t mul = sx::drop_mul(w), key = sx::drop_key(dseed, w);
+#pragma unroll
+              for (int P = 0; P < 2; ++P)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const unsigned long long g0 =
+                      (unsigned long long)((zoff + (long long)(row0 + 16 * P + 8 * h + tr) * p.ldc + col0 + tc) >> 2);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t bits = sx::drop_word_k(mul, key, g0 + 2 * j);
+                    const int i0 = 16 * P + 4 * j + 2 * h;
+                    f[i0] = (bits & 0xFFFFu) >= p16 ? f[i0] * keep_scale : 0.f;
+                    f[i0 + 1] = (bits >> 16) >= p16 ? f[i0 + 1] * keep_scale : 0.f;
+                  }
+                }
+            } else {
+#pragma unroll
+              for (int P = 0; P < 2; ++P)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const long long rbase = zoff + (long long)(row0 + 16 * P + 8 * h + tr) * p.ldc;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const unsigned long long e0 = (unsigned long long)(rbase + col0 + 8 * j + tc);
+                    const int i0 = 16 * P + 4 * j + 2 * h;
+                    f[i0] = sx::drop_keep1(dseed, e0, p16) ? f[i0] * keep_scale : 0.f;
+                    f[i0 + 1] = sx::drop_keep1(dseed, e0 + 1, p16) ? f[i0 + 1] * keep_scale : 0.f;
+                  }
+                }
+            }
+          }
+        };
         if (p.act == SX_ACT_GELU_BWD) {         // C = mask * acc * gelu'(h), h = the forward pre-activation (read-only)
+          apply_dropout();                      // (commutes with the gelu' factor; keeps h live only inside this block)
           float g[32];
           load_frag(reinterpret_cast<const float*>(p.preact), g, zoff, row0, col0);
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] *= sx::gelu_erf_grad(g[i]);
+          if (p.rowdot) {
+            // this thread's share of sum_n dU[m][n] * U[m][n]  (U = h - bias), rows [P][h]
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col = col0 + 8 * j + tc;
+              const float s0 = (p.rowdot_sub && col < p.N) ? p.rowdot_sub[col] : 0.f;
+              const float s1 = (p.rowdot_sub && col + 1 < p.N) ? p.rowdot_sub[col + 1] : 0.f;
+#pragma unroll
+              for (int P = 0; P < 2; ++P)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int i0 = 16 * P + 4 * j + 2 * h;
+                  rdot[2 * P + h] += f[i0] * (g[i0] - s0) + f[i0 + 1] * (g[i0 + 1] - s1);
+                }
+            }
+          }
+        } else if (p.act == SX_ACT_SOFTMAX_BWD) {
+          // dS = P * (mask * keep_scale * dPd - D), P = exp(min(s, clip) - lse) recomputed from the raw scores; zero
+          // where the forward clamped the score
+          apply_dropout();
+          float g[32];
+          load_frag(reinterpret_cast<const float*>(p.preact), g, zoff, row0, col0);
+#pragma unroll
+          for (int P = 0; P < 2; ++P)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float l2 = sm_lse[2 * P + h], dd = sm_dot[2 * P + h];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int i0 = 16 * P + 4 * j + 2 * h + e;
+                  const float sv = g[i0];
+                  const float pv = sx::ex2_approx(fminf(sv, p.clip) * 1.4426950408889634f - l2);
+                  f[i0] = sv > p.clip ? 0.f : pv * (f[i0] - dd);
+                }
+            }
         } else {
           if (p.preact) {
             if (CG2 && p.c_tma) tma_store(&tmP, f, row0, col0, z0, z1);
@@ -412,45 +507,7 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = sx::gelu_erf(f[i]);
           }
-        }
-        if (p.drop_p > 0.f) {
-          const float keep_scale = 1.f / (1.f - p.drop_p);
-          const uint32_t p16 = sx::drop_p16(p.drop_p);
-          const unsigned long long dseed = p.drop_seed + (p.drop_seed_dev ? *p.drop_seed_dev : 0ull);
-          if (((p.ldc | zoff) & 3) == 0) {
-            // rows start on a 4-element hash group: this thread's pair is always elements (tc&2, tc&2 + 1) of its
-            // group, i.e. one 32-bit word per pair with a per-thread constant multiplier / key
-            const int w = (tc >> 1) & 1;
-            const uint32_t mul = sx::drop_mul(w), key = sx::drop_key(dseed, w);
-#pragma unroll
-            for (int P = 0; P < 2; ++P)
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const unsigned long long g0 =
-                    (unsigned long long)((zoff + (long long)(row0 + 16 * P + 8 * h + tr) * p.ldc + col0 + tc) >> 2);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint32_t bits = sx::drop_word_k(mul, key, g0 + 2 * j);
-                  const int i0 = 16 * P + 4 * j + 2 * h;
-                  f[i0] = (bits & 0xFFFFu) >= p16 ? f[i0] * keep_scale : 0.f;
-                  f[i0 + 1] = (bits >> 16) >= p16 ? f[i0 + 1] * keep_scale : 0.f;
-                }
-              }
-          } else {
-#pragma unroll
-            for (int P = 0; P < 2; ++P)
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const long long rbase = zoff + (long long)(row0 + 16 * P + 8 * h + tr) * p.ldc;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const unsigned long long e0 = (unsigned long long)(rbase + col0 + 8 * j + tc);
-                  const int i0 = 16 * P + 4 * j + 2 * h;
-                  f[i0] = sx::drop_keep1(dseed, e0, p16) ? f[i0] * keep_scale : 0.f;
-                  f[i0 + 1] = sx::drop_keep1(dseed, e0 + 1, p16) ? f[i0 + 1] * keep_scale : 0.f;
-                }
-              }
-          }
+          apply_dropout();
         }
         if (p.round_tf32 && !p.c_bf16) {
 #pragma unroll
@@ -505,6 +562,16 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) {
         if constexpr (CG2) sx::mbar_arrive_leader(&tempty_bar[acc]);
         else sx::mbar_arrive(&tempty_bar[acc]);
+      }
+      if (p.rowdot) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = rdot[i];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          const int r = row0 + 16 * (i >> 1) + 8 * (i & 1) + tr;
+          if ((lane & 3) == 0 && r < p.M) atomicAdd(p.rowdot + zrow + r, v);
+        }
       }
     }
     if (p.amax) {
@@ -627,6 +694,9 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
                                 a->drop_p == 0.f && !a->amax),
              "sx_gemm: split_k > 1 needs accumulate=1 into fp32 C and a linear epilogue");
   SX_REQUIRE(!a->accumulate || a->c_dtype == SX_F32, "sx_gemm: accumulate needs fp32 C");
+  SX_REQUIRE(!a->round_tf32 || (!a->accumulate && p.split_k == 1),
+             "sx_gemm: round_tf32 cannot be combined with accumulate / split_k > 1 (a sum of rounded partials is not a TF32 "
+             "value): round the finished output instead");
   const long long tt = (long long)p.tiles_m * p.tiles_n * p.split_k * a->Z0 * a->Z1;
   SX_REQUIRE(tt < (1ll << 30), "sx_gemm: too many tiles");
   p.total_tiles = (int)tt;
@@ -643,6 +713,12 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
   p.act = a->act; p.accumulate = a->accumulate; p.preact = a->preact; p.amax = a->amax;
   p.addend = a->addend;
   p.colsum = a->colsum;
+  p.rowdot = a->rowdot; p.rowdot_sub = a->rowdot_sub;
+  p.row_lse = a->row_lse; p.row_dot = a->row_dot; p.clip = a->clip;
+  SX_REQUIRE(!a->rowdot || a->act == SX_ACT_GELU_BWD, "sx_gemm: rowdot needs SX_ACT_GELU_BWD");
+  SX_REQUIRE(a->act != SX_ACT_SOFTMAX_BWD || (a->preact && a->row_lse && a->row_dot && a->c_dtype == SX_F32 &&
+                                              !a->accumulate && a->split_k <= 1 && !a->bias),
+             "sx_gemm: SX_ACT_SOFTMAX_BWD needs the scores in `preact`, row_lse, row_dot, fp32 C, no bias, split_k=1");
   SX_REQUIRE(a->act != SX_ACT_GELU_BWD || (a->preact && a->c_dtype == SX_F32 && p.split_k == 1 && !a->accumulate),
              "sx_gemm: SX_ACT_GELU_BWD needs the fp32 pre-activation in `preact`, fp32 C, split_k=1, accumulate=0");
   SX_REQUIRE(!a->addend || (p.split_k == 1 && !a->accumulate && a->c_dtype == SX_F32), "sx_gemm: addend needs split_k=1, accumulate=0, fp32 C");
@@ -676,7 +752,7 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
       (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 && (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0)) {
     rc = make_out_map(&tc, a->C, a->N, a->M, a->Z0, a->Z1, a->ldc, a->c_stride_z0, a->c_stride_z1);
     if (rc) return rc;
-    if (a->preact && a->act != SX_ACT_GELU_BWD) {
+    if (a->preact && a->act != SX_ACT_GELU_BWD && a->act != SX_ACT_SOFTMAX_BWD) {
       rc = make_out_map(&tp, a->preact, a->N, a->M, a->Z0, a->Z1, a->ldc, a->c_stride_z0, a->c_stride_z1);
       if (rc) return rc;
     }

@@ -122,21 +122,23 @@ static int sm_count_cached() {
   return n[dev];
 }
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: done once per (kernel, device)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-(kernel, device) setting: done once for each pair (the
+// kernels are template instantiations that share one function-pointer TYPE, so the cache is keyed by pointer VALUE)
 template <typename K>
 static cudaError_t set_max_smem_once(K kern, int bytes) {
   static std::mutex mu;
-  static bool done[64] = {false};
+  static const void* seen[64 * 32];
+  static int nseen = 0;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  const void* key = reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(kern) * 64u + (uintptr_t)(dev & 63));
   std::lock_guard<std::mutex> lk(mu);
-  if (!done[dev]) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    done[dev] = true;
-  }
+  for (int i = 0; i < nseen; ++i)
+    if (seen[i] == key) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  if (nseen < 64 * 32) seen[nseen++] = key;
   return cudaSuccess;
 }
 

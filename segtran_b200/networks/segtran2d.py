@@ -222,6 +222,7 @@ class Segtran2d(SegtranInitWeights):
             self._pos_cache_key, self._pos_cache = key, idx
         voxels_pos = self._pos_cache.unsqueeze(0).expand(B0, -1, -1)
         fused = self.voxel_fusion(vfeat, voxels_pos, None if vmask is None else vmask.unsqueeze(2), grid)
+        ops.grad_ready(fused, list(self.out_fpn_bridgeconv.parameters()) + list(self.out_conv.parameters()))   # backward past the head
         self.layers_attn_scores = self.voxel_fusion.layers_attn_scores
         for i in range(self.num_translayers):
             self.feature_maps.append(self.voxel_fusion.translayers[i].attention_scores)

@@ -257,6 +257,7 @@ class Segtran3d(SegtranInitWeights):
             self._pos_cache_key, self._pos_cache = key, idx
         voxels_pos = self._pos_cache.unsqueeze(0).expand(B, -1, -1)  # one set of positions, shared by the batch
         fused = self.voxel_fusion(vfeat, voxels_pos, None if vmask is None else vmask.unsqueeze(2), grid)
+        ops.grad_ready(fused, list(self.out_fpn_bridgeconv3d.parameters()) + list(self.out_conv3d.parameters()))   # backward past the head
         self.layers_attn_scores = self.voxel_fusion.layers_attn_scores
         self.orig_feat_shape = grid
         if self.out_fpn_do_dropout and self.training:

@@ -224,30 +224,62 @@ class ExpandedFeatTrans(nn.Module):
             w = self.first_linear.weight.data
             w[:Fd, :Fd] = w[:Fd, :Fd] * 0.5 + eye.to(w)
 
+    def _can_fold(self):
+        return self.has_FFN and isinstance(self.output, MMPrivateOutput) and isinstance(self.intermediate, MMSharedMid) \
+            and self.first_linear.bias is None and self.first_linear.weight.shape[1] % 4 == 0 and self.feat_dim % 4 == 0
+
+    def supports_fused_attention(self):
+        """The expansion block whose P.V / mid / output chain hangs off one autograd node (ops.squeeze_out_fused)."""
+        return self.has_FFN and isinstance(self.output, MMPrivateOutput) and isinstance(self.intermediate, MMSharedMid)
+
+    def _value_bank(self, input_feat):
+        """V' = (x Wv^T) Wm^T, the value bank already pushed through MMSharedMid's Linear (see forward)."""
+        M, mid = self.num_modes, self.intermediate
+        B, U2 = input_feat.shape[0], input_feat.shape[1]
+        if self._can_fold():
+            return ops.folded_value_bank(input_feat, self.first_linear.weight, mid.shared_linear.weight, M)
+        v = ops.linear(input_feat, self.first_linear.weight, self.first_linear.bias)     # [B,U2,M*F]
+        return ops.linear(v.view(B, U2, M, self.feat_dim), mid.shared_linear.weight).view(B, U2, M * self.feat_dim)
+
+    def _norm_aggregate(self, y):
+        p = self.output.dropout.p if self.training else 0.0
+        ln = self.output.resout_norm_layer
+        f2s = self.feat_softaggr.feat2score
+        return ops.ln_softaggr(y, ln.weight, ln.bias, f2s.weight, f2s.bias, drop_p=p,
+                               seed=ops.new_dropout_seed(y.device) if p > 0 else 0)
+
+    def forward_from_qk(self, input_feat, q, k, clip, att_p, diag):
+        """Fused attention entry: q [Bq,U1,M*d], k [B,U2,M*d] (projected, TF32-rounded) instead of the probabilities —
+        scores, clamp, softmax and attention dropout run inside ops.squeeze_out_fused (csrc/sx_attn.cu)."""
+        mid = self.intermediate
+        vp = self._value_bank(input_feat)
+        p = mid.dropout.p if self.training else 0.0
+        gl = self.output.group_linear
+        dev = vp.device
+        y = ops.squeeze_out_fused(q, k, vp, self.num_modes, clip, att_p, ops.new_dropout_seed(dev) if att_p > 0 else 0,
+                                  mid.shared_linear.bias, p, ops.new_dropout_seed(dev) if p > 0 else 0, gl.weight, gl.bias,
+                                  diag)
+        return self._norm_aggregate(y)
+
     def forward(self, input_feat, attention_probs, in_geoshape=None):
         """input_feat [B,U2,C]; attention_probs [B,M,U1,U2] -> [B,U1,F]."""
         M = self.num_modes
-        fold = self.has_FFN and isinstance(self.output, MMPrivateOutput) and isinstance(self.intermediate, MMSharedMid) \
-            and self.first_linear.bias is None and self.first_linear.weight.shape[1] % 4 == 0 and self.feat_dim % 4 == 0
-        if not fold:
+        folded = self.supports_fused_attention()
+        if not folded:
             v = ops.linear(input_feat, self.first_linear.weight, self.first_linear.bias)     # [B,U2,M*F]
         if not self.has_FFN:
             if M != 1:
                 _unsupported("the no-FFN branch with more than one mode (Polyformer)")
             u = ops.attn_pv(attention_probs, v, M)                                           # [B,M,U1,F]
             return ops.layer_norm(u[:, 0], self.first_norm_layer.weight, self.first_norm_layer.bias)
-        if isinstance(self.output, MMPrivateOutput) and isinstance(self.intermediate, MMSharedMid):
+        if folded:
             # (P V) Wm^T = P (V Wm^T): push the value bank (U2 rows) through the shared mid Linear instead of the
             # fused tokens (U1 rows), and fuse MMSharedMid's bias + GELU + dropout into the P.V epilogue.  U itself
             # is only needed by the (discarded) residual of MMPrivateOutput, so it is never materialised.
             # With a bias-free value projection the two Linears on the bank fold into one weight-space product
             # W'_m = Wm Wv_m (batch-independent), so the bank is projected once.
             mid = self.intermediate
-            B, U2 = input_feat.shape[0], input_feat.shape[1]
-            if fold:
-                vp = ops.folded_value_bank(input_feat, self.first_linear.weight, mid.shared_linear.weight, M)
-            else:
-                vp = ops.linear(v.view(B, U2, M, self.feat_dim), mid.shared_linear.weight).view(B, U2, M * self.feat_dim)
+            vp = self._value_bank(input_feat)
             p = mid.dropout.p if self.training else 0.0
             # ... and MMPrivateOutput's grouped Linear rides in the same autograd node (its backward fuses GELU' and
             # the dropout mask into the dG GEMM epilogue)
@@ -258,11 +290,7 @@ class ExpandedFeatTrans(nn.Module):
             u = ops.attn_pv(attention_probs, v, M)
             g = self.intermediate(u)
             y = self.output(g, u)
-        p = self.output.dropout.p if self.training else 0.0
-        ln = self.output.resout_norm_layer
-        f2s = self.feat_softaggr.feat2score
-        return ops.ln_softaggr(y, ln.weight, ln.bias, f2s.weight, f2s.bias, drop_p=p,
-                               seed=ops.new_dropout_seed(y.device) if p > 0 else 0)
+        return self._norm_aggregate(y)
 
 
 class CrossAttFeatTrans(nn.Module):
@@ -316,8 +344,14 @@ class CrossAttFeatTrans(nn.Module):
     def _diag_values(self):
         if self._diag is None:
             return 0.0, 0
-        m, c = self._diag.tolist()
+        m, c = self._diag.tolist()[:2]
         return (m if m > -1e38 else 0.0), int(c)
+
+    @property
+    def lower_clamp_ambiguous_rows(self):
+        """Rows of fused-attention calls where the reference's LOWER clamp could have changed the result (a row whose
+        maximum is below -(clip-104) in a call whose global maximum exceeded +clip; see csrc/sx_attn.cu).  Expected 0."""
+        return 0 if self._diag is None else int(self._diag.tolist()[2])
 
     @property
     def max_attn(self):
@@ -337,10 +371,18 @@ class CrossAttFeatTrans(nn.Module):
         k = ops.linear(in_key, self.key.weight, self.key.bias)
         dev = q.device
         if self._diag is None or self._diag.device != dev:
-            self._diag = torch.tensor([-3.0e38, 0.0], device=dev)
+            self._diag = torch.tensor([-3.0e38, 0.0, 0.0], device=dev)
+        p = self.att_dropout.p if self.training else 0.0
+        diag_call = self.training and (self.call_count + 1) % self.attn_diag_cycles == 0     # prints avg-attn: needs S
+        if ops.attn_fusion_enabled() and not self.keep_attn_scores and not diag_call and q.is_cuda and \
+                self.attention_mode_dim % 4 == 0 and self.out_trans.supports_fused_attention():
+            # fused squeeze-out attention: scores / clamp / softmax / dropout inside one tcgen05 kernel
+            self.attention_scores = None
+            if self.training:
+                self.call_count += 1
+            return self.out_trans.forward_from_qk(in_key, q, k, float(self.attn_clip), p, self._diag)
         amax = torch.full((1,), -3.0e38, device=dev)
         s = ops.attn_scores(q, k, M, amax)                                   # [B,M,U1,U2], max tracked on device
-        p = self.att_dropout.p if self.training else 0.0
         probs = ops.softmax(s, amax, float(self.attn_clip), p, ops.new_dropout_seed(dev) if p > 0 else 0, self._diag)
         self.attention_scores = s if self.keep_attn_scores else None
         if self.training:
@@ -350,7 +392,7 @@ class CrossAttFeatTrans(nn.Module):
                     avg = float(s.sum() / (s > 0).sum().clamp_min(1))
                 mx, cc = self._diag_values()
                 print("max-attn: {:.2f}, avg-attn: {:.2f}, clamp-count: {}".format(mx, avg, cc))
-                self._diag = torch.tensor([-3.0e38, 0.0], device=dev)
+                self._diag = torch.tensor([-3.0e38, 0.0, 0.0], device=dev)
         return self.out_trans(in_key, probs)
 
 
@@ -394,7 +436,7 @@ class SqueezedAttFeatTrans(nn.Module):
             rb = ops.scale(ops.matvec(q1[0], t.key.bias), 1.0 / math.sqrt(C))
         dev = in_feat.device
         if t._diag is None or t._diag.device != dev:
-            t._diag = torch.tensor([-3.0e38, 0.0], device=dev)
+            t._diag = torch.tensor([-3.0e38, 0.0, 0.0], device=dev)
         amax = torch.full((1,), -3.0e38, device=dev)
         s = ops.attn_scores(qw, in_feat, 1, amax, rb)                                  # [B,1,A,N]
         p = t.att_dropout.p if t.training else 0.0
@@ -416,6 +458,7 @@ class SqueezedAttFeatTrans(nn.Module):
             att = self._in_squeeze_reassociated(in_feat)
         else:
             att = t(self.attractors, in_feat)       # attractors are batch-invariant: projected once
+        ops.grad_ready(att, self.ator_out_trans.parameters())       # backward past `att`: the squeeze-out weights are final
         out = self.ator_out_trans(in_feat, att)
         self.attention_scores = self.ator_out_trans.attention_scores
         return out
@@ -522,6 +565,7 @@ class SegtranFusionEncoder(nn.Module):
             p = self.dropout.p if (self.training and i == 0) else 0.0
             h = ops.prologue(x, ln.weight, ln.bias, pe, float(self.pos_code_weight), mask, p,
                              ops.new_dropout_seed(x.device) if p > 0 else 0)
+            ops.grad_ready(h, layer.parameters())                   # backward past `h`: this layer's weights are final
             x = layer(h, pos_biases=None)
             self.layers_vfeat.append(x)
             if self.use_attn_consist_loss:

@@ -49,6 +49,31 @@ def set_grad_sink(on: bool):
     _GRAD_SINK = bool(on)
 
 
+# Gradient-ready milestones (parallel.GradBucket(milestones=True)): modules mark tensors at layer boundaries; when the
+# backward pass reaches such a tensor every node created after it has already run (autograd executes in descending
+# creation order), so the gradients of the parameters used after that point are final and their all-reduce can start.
+_GRAD_READY_CB = None
+
+
+def set_grad_ready_callback(fn):
+    global _GRAD_READY_CB
+    _GRAD_READY_CB = fn
+
+
+def grad_ready(t: torch.Tensor, params):
+    """When backward reaches `t`, announce that the gradients of `params` are final.  No-op without a callback."""
+    if _GRAD_READY_CB is None or not isinstance(t, torch.Tensor) or not t.requires_grad:
+        return
+    ps = list(params)
+    cb = _GRAD_READY_CB
+
+    def hook(_g):
+        cb(ps)
+        return None
+
+    t.register_hook(hook)
+
+
 def _grad_target(p):
     if not _GRAD_SINK or not isinstance(p, torch.nn.Parameter) or p.grad is None:
         return None
@@ -229,7 +254,8 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
                preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
                amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
                reduce_z1: bool = False, addend: Optional[torch.Tensor] = None,
-               gelu_bwd: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+               gelu_bwd: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
+               rowdot=None, softmax_bwd=None) -> torch.Tensor:
     """a [..., M, K], b [..., N, K] (strided fp32 views; either dim may be the contiguous one) ->
     out [z1, z0, M, N] fp32.  With reduce_z1 the z1 batch dim is summed into one output (atomic accumulate)."""
     _req_cuda(a, b, out, bias, preact, amax)
@@ -247,7 +273,8 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
             raise L.SxError("gemm_nt: batch dims do not broadcast")
     oz1 = 1 if reduce_z1 else Z1
     fresh = out is None
-    linear_epi = (not gelu) and preact is None and drop_p == 0.0 and amax is None and gelu_bwd is None
+    linear_epi = (not gelu) and preact is None and drop_p == 0.0 and amax is None and gelu_bwd is None and \
+        softmax_bwd is None
     if split_k is None:
         split_k = _pick_split_k(M, N, K, Z0 * Z1) if (linear_epi and (fresh or accumulate or reduce_z1)) else 1
     if fresh:
@@ -265,7 +292,10 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
     g.B = _operand(b4, Z1, Z0, "B")
     g.C = o4.data_ptr()
     g.c_dtype = L.SX_F32
-    g.round_tf32 = 1 if (round_out and _PRECISION == "tf32") else 0
+    # a split-K / accumulating launch adds partial sums in memory: rounding each partial to TF32 would leave a sum that is
+    # NOT a TF32 value (the tensor core would then truncate it), so the rounding becomes a pass over the finished output
+    round_after = round_out and _PRECISION == "tf32" and (split_k > 1 or accumulate or reduce_z1)
+    g.round_tf32 = 1 if (round_out and _PRECISION == "tf32" and not round_after) else 0
     g.ldc = o4.stride(-2)
     g.c_stride_z0 = o4.stride(1) if o4.shape[1] > 1 else 0
     g.c_stride_z1 = 0 if reduce_z1 else (o4.stride(0) if o4.shape[0] > 1 else 0)
@@ -300,7 +330,23 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
         if addend.dtype != torch.float32 or tuple(addend.shape[-2:]) != (M, N) or _as4(addend).stride() != o4.stride():
             raise L.SxError("gemm_nt: addend must be an fp32 tensor in the output's layout")
         g.addend = addend.data_ptr()
+    if rowdot is not None:                   # (D [Z1,Z0,M] accumulated into, sub [N] or None): see SX_ACT_GELU_BWD / rowdot
+        D, sub = rowdot
+        if gelu_bwd is None or D.numel() != Z1 * Z0 * M or not D.is_contiguous():
+            raise L.SxError("gemm_nt: rowdot needs gelu_bwd and a contiguous [Z1,Z0,M] accumulator")
+        g.rowdot = D.data_ptr()
+        g.rowdot_sub = _ptr(sub)
+    if softmax_bwd is not None:              # (S raw scores in the output's layout, lse [Z1,Z0,M], D [Z1,Z0,M], clip)
+        Sx, lse, D, clip = softmax_bwd
+        if gelu or gelu_bwd is not None or preact is not None or _as4(Sx).stride() != o4.stride() or \
+                lse.numel() != Z1 * Z0 * M or D.numel() != Z1 * Z0 * M:
+            raise L.SxError("gemm_nt: softmax_bwd needs the scores in the output's layout and per-row lse / dot vectors")
+        g.act = L.SX_ACT_SOFTMAX_BWD
+        g.preact = Sx.data_ptr()
+        g.row_lse, g.row_dot, g.clip = lse.data_ptr(), D.data_ptr(), float(clip)
     L.call("sx_gemm", C.byref(g), _stream())
+    if round_after and fresh:                # (caller-provided accumulators are gradient buffers: never rounded)
+        L.call("sx_convert", out.data_ptr(), L.SX_F32, out.numel(), out.data_ptr(), L.SX_F32, 1, _stream())
     return out
 
 
@@ -322,13 +368,15 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = N
             preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
             amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
             reduce_z1: bool = False, gelu_bwd: Optional[torch.Tensor] = None,
-            addend: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+            addend: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
+            rowdot=None, softmax_bwd=None) -> torch.Tensor:
     """C[..., m, n] = epilogue(alpha * sum_k a[..., m, k] b[..., n, k]) on the tcgen05 GEMM.  In the default
     precision this is one launch; in 'tf32x3' it is three passes on the hi/lo operand splits."""
     if _PRECISION == "tf32":
         return _gemm_nt_1(a, b, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
                           accumulate=accumulate, split_k=split_k, amax=amax, drop_p=drop_p, seed=seed,
-                          round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd, addend=addend, colsum=colsum)
+                          round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd, addend=addend, colsum=colsum,
+                          rowdot=rowdot, softmax_bwd=softmax_bwd)
     _req_cuda(a, b)
     ah, al = _tf32_split(a)
     bh, bl = _tf32_split(b)
@@ -348,7 +396,7 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = N
     _gemm_nt_1(ah, bl, out=part, alpha=alpha, split_k=1, round_out=False, addend=part)
     return _gemm_nt_1(ah, bh, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
                       split_k=1, amax=amax, drop_p=drop_p, seed=seed, round_out=False, addend=part, gelu_bwd=gelu_bwd,
-                      colsum=colsum)
+                      colsum=colsum, rowdot=rowdot, softmax_bwd=softmax_bwd)
 
 
 def _pad4(n: int) -> int:
@@ -389,7 +437,8 @@ def round_tf32(x: torch.Tensor) -> torch.Tensor:
         # parameters managed by train.FlatBertAdam carry a TF32-rounded twin that the optimiser kernel keeps current
         # (`_sx_tf32`); it is valid as long as nobody modified the parameter in place since (version counter)
         r = getattr(x, "_sx_tf32", None)
-        if r is not None and getattr(x, "_sx_tf32_version", -1) == x._version:
+        if r is not None and getattr(x, "_sx_tf32_version", -1) == x._version and \
+                getattr(x, "_sx_tf32_ptr", None) == x.data_ptr():
             return r
     x = x.contiguous()
     if _PRECISION != "tf32":
@@ -834,6 +883,113 @@ class _AttnPVGeluGroupLinear(torch.autograd.Function):
 
 def attn_pv_gelu_group_linear(P, v, M, bm, drop_p, seed, Wo, bo):
     return _AttnPVGeluGroupLinear.apply(P, v, M, bm, drop_p, seed, Wo, bo)
+
+
+# Fused squeeze-out attention (opt-out: set_attn_fusion(False)): scores + clamp + softmax + attention dropout run in
+# csrc/sx_attn.cu (S never reaches HBM in inference; in training the raw scores are kept for the backward, which
+# recomputes P in the epilogue of the dP GEMM instead of running a softmax-backward pass over P and dP).
+_ATTN_FUSION = True
+
+
+def set_attn_fusion(on: bool):
+    global _ATTN_FUSION
+    _ATTN_FUSION = bool(on)
+
+
+def attn_fusion_enabled() -> bool:
+    return _ATTN_FUSION and _PRECISION == "tf32"          # the 3-pass validation mode keeps the unfused fp32-grade products
+
+
+class _SqueezeOutFused(torch.autograd.Function):
+    """Y[b,m] = dropout(gelu(P[b,m] V'[b,:,m] + bm)) Wo[m]^T + bo[m]  with  P = dropout(softmax(min(Q K^T/sqrt(d), clip)))
+    — CrossAttFeatTrans.forward (segtran_shared.py:566-605) + ExpandedFeatTrans up to MMPrivateOutput's Linear
+    (:447, :243-245, :267) as ONE autograd node:
+      forward : sx_attn_probs_fwd (tcgen05 scores -> in-TMEM softmax -> P)  ->  P.V' GEMM (bias/GELU/dropout epilogue)
+                -> grouped output Linear;
+      backward: dH GEMM (GELU'/dropout epilogue; it also accumulates the softmax row term D = sum_f dU_f U_f and the
+                bias-gradient column sums) -> dS GEMM (dP = dH V'^T with the softmax backward in its epilogue: P is
+                recomputed from the saved raw scores, dP never exists in memory) -> dV', dQ, dK, dWo, dbo products."""
+
+    @staticmethod
+    def forward(ctx, q, k, vp, M, clip, att_p, att_seed, bm, hid_p, hid_seed, Wo, bo, diag):
+        B, U2 = k.shape[0], k.shape[1]
+        U1 = q.shape[1]
+        Fd = vp.shape[-1] // M
+        q = q.contiguous()
+        k = k.contiguous()
+        need_bwd = any(ctx.needs_input_grad)
+        P, S, lse, _rowmax, _stat = attn_probs_fused(q, k, M, clip, att_p, att_seed, diag, need_scores=need_bwd)
+        vv = vp.view(B, U2, M, Fd).permute(0, 2, 3, 1)
+        G = torch.empty((B, M, U1, Fd), device=P.device, dtype=torch.float32)
+        H = torch.empty_like(G)
+        gemm_nt(P, vv, out=G, bias=bm, gelu=True, preact=H, drop_p=hid_p, seed=hid_seed)
+        Wr = round_tf32(Wo).reshape(M, Fd, Fd)
+        Y = torch.empty_like(G)
+        gemm_nt(G, Wr.unsqueeze(0), out=Y, bias=bo.reshape(1, M, Fd), round_out=False)
+        ctx.save_for_backward(q, k, P, S, lse, vp, H, G, Wr)
+        ctx.meta = (M, Fd, float(clip), att_p, hid_p, bm is not None, Wo.shape)
+        ctx.seeds = (att_seed, hid_seed)
+        ctx.leaves = (bm, Wo, bo)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        q, k, P, S, lse, vp, H, G, Wr = ctx.saved_tensors
+        M, Fd, clip, att_p, hid_p, has_bm, wshape = ctx.meta
+        att_seed, hid_seed = ctx.seeds
+        bm, Wo, bo = ctx.leaves
+        B, _, U1, U2 = P.shape
+        Bq, d = q.shape[0], q.shape[-1] // M
+        dY = dY.contiguous()
+        dq = dk = dvp = dbm = dW = dbo = None
+        # dH = mask * (dY Wo) * gelu'(H); the same epilogue accumulates D[b,m,n] = sum_f dH U (U = H - bm = P V') and the
+        # column sums of dH (MMSharedMid's bias gradient)
+        dH = torch.empty_like(H)
+        dbm_buf = None
+        if has_bm and ctx.needs_input_grad[7]:
+            tgt = _grad_target(bm)
+            dbm_buf = tgt if tgt is not None else _zeros((Fd,), dY.device)
+            dbm = None if tgt is not None else dbm_buf
+        need_ds = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        D = _zeros((B, M, U1), dY.device) if need_ds else None
+        gemm_nt(dY, Wr.transpose(-1, -2).unsqueeze(0), out=dH, gelu_bwd=H, drop_p=hid_p, seed=hid_seed, colsum=dbm_buf,
+                rowdot=None if D is None else (D, bm))
+        if ctx.needs_input_grad[10]:
+            tgt = _grad_target(Wo)
+            if tgt is not None:
+                gemm_nt(dY.transpose(-1, -2), G.transpose(-1, -2), out=tgt.view(1, M, Fd, Fd), reduce_z1=True,
+                        accumulate=True, round_out=False)
+            else:
+                dW = gemm_nt(dY.transpose(-1, -2), G.transpose(-1, -2), reduce_z1=True, round_out=False).view(wshape)
+        if ctx.needs_input_grad[11]:
+            tgt = _grad_target(bo)
+            dbo_buf = tgt if tgt is not None else _zeros((M * Fd,), G.device)
+            L.call("sx_colsum_batched", dY.data_ptr(), B, M * U1 * Fd, M, U1 * Fd, U1, Fd, Fd, dbo_buf.data_ptr(), _stream())
+            dbo = None if tgt is not None else dbo_buf
+        if ctx.needs_input_grad[2]:
+            dvp = torch.empty_like(vp)
+            gemm_nt(P.transpose(-1, -2), dH.transpose(-1, -2), out=dvp.view(B, U2, M, Fd).permute(0, 2, 1, 3),
+                    round_out=False)
+        if need_ds:
+            # dS = P * (mask_att * dPd - D) with dPd = dH V'^T never written: the softmax backward is the GEMM's epilogue
+            dS = torch.empty_strided(P.size(), P.stride(), device=P.device, dtype=torch.float32)
+            gemm_nt(dH, vp.view(B, U2, M, Fd).permute(0, 2, 1, 3), out=dS, drop_p=att_p, seed=att_seed,
+                    softmax_bwd=(S, lse, D, clip))
+            scale = 1.0 / math.sqrt(d)
+            if ctx.needs_input_grad[0]:
+                bcast = Bq == 1 and B > 1
+                dq = _zeros_like(q) if bcast else torch.empty_like(q)
+                gemm_nt(dS, k.view(B, U2, M, d).permute(0, 2, 3, 1), out=dq.view(Bq, U1, M, d).permute(0, 2, 1, 3),
+                        alpha=scale, round_out=False, reduce_z1=bcast, split_k=1)
+            if ctx.needs_input_grad[1]:
+                dk = torch.empty_like(k)
+                gemm_nt(dS.transpose(-1, -2), q.view(Bq, U1, M, d).permute(0, 2, 3, 1),
+                        out=dk.view(B, U2, M, d).permute(0, 2, 1, 3), alpha=scale, round_out=False)
+        return dq, dk, dvp, None, None, None, None, dbm, None, None, dW, dbo, None
+
+
+def squeeze_out_fused(q, k, vp, M, clip, att_p, att_seed, bm, hid_p, hid_seed, Wo, bo, diag):
+    return _SqueezeOutFused.apply(q, k, vp, M, clip, att_p, att_seed, bm, hid_p, hid_seed, Wo, bo, diag)
 
 
 class _LayerNorm(torch.autograd.Function):

@@ -22,7 +22,7 @@ _ALIGN = 64          # elements (256 bytes of fp32)
 
 class GradBucket:
     def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None, overlap_chunks: int = 0,
-                 direct_accumulate: bool = False):
+                 direct_accumulate: bool = False, milestones: bool = False):
         seen, self.params = set(), []
         for p in params:                      # tied parameters (query/key) appear once
             if p.requires_grad and id(p) not in seen:
@@ -51,6 +51,18 @@ class GradBucket:
             ops.set_grad_sink(True)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        # milestones: the modules announce "the gradients of these parameters are final" from tensor hooks placed at layer
+        # boundaries (ops.grad_ready); each announcement starts the all-reduce of the covered bucket ranges on the side
+        # stream while the rest of backward is still running.  Works with direct_accumulate (no AccumulateGrad hooks are
+        # needed) and inside a captured CUDA graph (the side stream forks from and re-joins the capturing stream).
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._sent = [False] * len(self.params)
+        self._milestones = bool(milestones) and self.world > 1
+        if self._milestones:
+            if overlap_chunks > 1:
+                raise ValueError("GradBucket: milestones and overlap_chunks are mutually exclusive")
+            from . import ops
+            ops.set_grad_ready_callback(self.ready)
         self._comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         # NCCL averages inside the collective (no extra pass over the bucket); gloo has no AVG -> SUM then scale
         self._avg = self.world > 1 and dist.get_backend(process_group) == "nccl"
@@ -88,6 +100,38 @@ class GradBucket:
         else:
             self._works.append(dist.all_reduce(view, op=self._op, group=self.group, async_op=True))
 
+    def _span(self, i):
+        n = self.params[i].numel()
+        return self.offsets[i], self.offsets[i] + (n + _ALIGN - 1) // _ALIGN * _ALIGN
+
+    def _send_params(self, idx):
+        """all-reduce the bucket ranges of the (sorted) parameter indices, merging neighbours into one call"""
+        runs = []
+        for i in idx:
+            lo, hi = self._span(i)
+            if runs and runs[-1][1] == lo:
+                runs[-1][1] = hi
+            else:
+                runs.append([lo, hi])
+            self._sent[i] = True
+        if not runs:
+            return
+        if self._comm is not None:
+            self._comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm):
+                for lo, hi in runs:
+                    self._works.append(dist.all_reduce(self.flat[lo:hi], op=self._op, group=self.group, async_op=True))
+        else:
+            for lo, hi in runs:
+                self._works.append(dist.all_reduce(self.flat[lo:hi], op=self._op, group=self.group, async_op=True))
+
+    def ready(self, params):
+        """The gradients of `params` are final for this step: start exchanging them now (milestone mode)."""
+        if not self._milestones:
+            return
+        self._send_params(sorted({self._index[id(p)] for p in params
+                                  if id(p) in self._index and not self._sent[self._index[id(p)]]}))
+
     def _on_grad_ready(self, p):
         c = self._chunks[p._sx_chunk]
         c["left"] -= 1
@@ -99,6 +143,8 @@ class GradBucket:
         self.flat.zero_()
         for c in self._chunks:
             c["left"], c["sent"] = c["n"], False
+        if self._milestones:
+            self._sent = [False] * len(self.params)
 
     def reattach(self):
         """Call if something replaced p.grad (e.g. zero_grad(set_to_none=True))."""
@@ -110,6 +156,9 @@ class GradBucket:
     def allreduce_async(self):
         """Average the bucket over ranks; returns immediately (the transfer runs on a side stream on GPUs)."""
         if self.world == 1:
+            return
+        if self._milestones:                  # whatever no milestone has covered (e.g. the first layer's norm / pos-code)
+            self._send_params([i for i in range(len(self.params)) if not self._sent[i]])
             return
         if self._chunks:                      # overlap mode: send whatever backward has not triggered (unused params)
             for c in self._chunks:
@@ -129,7 +178,7 @@ class GradBucket:
         """Make the averaged gradients visible to the current stream (call before the optimizer step)."""
         if self.world == 1:
             return
-        if self._chunks:
+        if self._chunks or self._milestones:
             if self._comm is not None:
                 with torch.cuda.stream(self._comm):
                     for w in self._works:

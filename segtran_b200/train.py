@@ -100,6 +100,14 @@ class FlatBertAdam:
             bucket = GradBucket([p for gr in groups for p in gr["params"]])
         self.bucket = bucket
         self.params: List[torch.nn.Parameter] = bucket.params
+        in_bucket = {id(p) for p in self.params}
+        missing = [p for gr in groups for p in gr["params"] if p.requires_grad and id(p) not in in_bucket]
+        if missing:
+            # such parameters would silently never be updated and would be left out of the --gradclip norm
+            raise ValueError("FlatBertAdam: %d trainable parameter(s) of the param groups (%d elements) are not in the "
+                             "gradient bucket; build the GradBucket from the same parameters (e.g. GradBucket(p for g in "
+                             "groups for p in g['params'])) or give those parameters to a second optimiser"
+                             % (len(missing), sum(p.numel() for p in missing)))
         for p in self.params:
             if id(p) not in per:
                 raise ValueError("FlatBertAdam: the gradient bucket holds a parameter that is in no param group")
@@ -140,6 +148,15 @@ class FlatBertAdam:
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)         # pre-clip global norm of the last step
         self.hyper = dict(b1=b1, b2=b2, e=e, max_grad_norm=max_grad_norm, grad_clip=grad_clip, warmup=warmup,
                           t_total=t_total, schedule=schedule)
+        # torch.optim.Optimizer-shaped view of the configuration (what the reference's checkpoints and LR logging read)
+        self.param_groups = []
+        pos = {id(p): i for i, p in enumerate(self.params)}
+        for gr in groups:
+            glr = gr.get("lr", lr)
+            self.param_groups.append({"params": [p for p in gr["params"] if id(p) in pos], "lr": float(glr),
+                                      "weight_decay": float(gr.get("weight_decay", weight_decay)), "schedule": schedule,
+                                      "warmup": warmup, "t_total": t_total, "b1": b1, "b2": b2, "e": e,
+                                      "max_grad_norm": max_grad_norm})
 
     def refresh_rounded(self):
         L.call("sx_convert", self.flat_p.data_ptr(), L.SX_F32, self.flat_p.numel(), self.flat_r.data_ptr(), L.SX_F32, 1,
@@ -147,6 +164,7 @@ class FlatBertAdam:
         for p, off in zip(self.params, self.bucket.offsets):
             p._sx_tf32 = self.flat_r[off:off + p.numel()].view_as(p)
             p._sx_tf32_version = p._version
+            p._sx_tf32_ptr = p.data_ptr()
 
     def zero_grad(self, set_to_none: bool = False):
         """One memset of the bucket (the .grad views stay attached; set_to_none is ignored on purpose)."""
@@ -161,16 +179,62 @@ class FlatBertAdam:
                h["e"], float(h["grad_clip"]), float(h["max_grad_norm"]), float(h["warmup"]), int(h["t_total"]), sched,
                self.step_count.data_ptr(), self._sumsq.data_ptr(), self._coef.data_ptr(), self._lr_eff.data_ptr(),
                self.grad_norm.data_ptr(), ops._stream())
+        # the kernel has just rewritten the TF32 twin of EVERY parameter: twins invalidated by an in-place torch edit since
+        # the last step (e.g. load_state_dict, which bumps the version counters) are valid again
+        for p in self.params:
+            if p._sx_tf32_version != p._version:
+                p._sx_tf32_version = p._version
 
     def get_lr(self):
         """Scheduled learning rates of the LAST step (one device read; the reference's get_lr(), optimization.py:75-88)."""
         return self._lr_eff.tolist()
 
     def state_dict(self):
-        return {"step": int(self.step_count.item()), "next_m": self.flat_m.clone(), "next_v": self.flat_v.clone(),
-                "hyper": dict(self.hyper)}
+        """torch.optim.Optimizer layout (what the reference stores as 'optim_state', train3d.py:398): per-parameter
+        {'step', 'next_m', 'next_v'} keyed by the parameter's index, plus the param_groups with index lists."""
+        step = int(self.step_count.item())
+        state, idx = {}, {id(p): i for i, p in enumerate(self.params)}
+        for i, (p, off) in enumerate(zip(self.params, self.bucket.offsets)):
+            n = p.numel()
+            state[i] = {"step": step, "next_m": self.flat_m[off:off + n].view_as(p).clone(),
+                        "next_v": self.flat_v[off:off + n].view_as(p).clone()}
+        groups = [{k: (v if k != "params" else [idx[id(p)] for p in v]) for k, v in g.items()} for g in self.param_groups]
+        return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, sd):
+        """Accepts the layout above (also as written by the reference's BertAdam for the same parameter order) and the
+        round-1 flat layout {'step', 'next_m', 'next_v'}."""
+        if "state" in sd:
+            st = sd["state"]
+            if len(st) > len(self.params):
+                raise ValueError("FlatBertAdam.load_state_dict: %d parameter states for %d parameters" % (len(st), len(self.params)))
+            steps = set()
+            for i, (p, off) in enumerate(zip(self.params, self.bucket.offsets)):
+                e = st.get(i, st.get(str(i)))
+                if e is None:                      # the reference keeps no state for parameters that never got a gradient
+                    continue
+                n = p.numel()
+                if e["next_m"].numel() != n or e["next_v"].numel() != n:
+                    raise ValueError("FlatBertAdam.load_state_dict: parameter %d has %d elements, the checkpoint %d"
+                                     % (i, n, e["next_m"].numel()))
+                self.flat_m[off:off + n].copy_(e["next_m"].reshape(-1))
+                self.flat_v[off:off + n].copy_(e["next_v"].reshape(-1))
+                steps.add(int(e["step"]))
+            if steps:
+                self.step_count.fill_(max(steps))
+            for g_new, g_old in zip(self.param_groups, sd.get("param_groups", [])):
+                for k in ("lr", "weight_decay"):
+                    if k in g_old:
+                        g_new[k] = float(g_old[k])
+            pos = {id(p): i for i, p in enumerate(self.params)}
+            for g in self.param_groups:
+                for p in g["params"]:
+                    self._lr[pos[id(p)]] = g["lr"]
+                    self._wd[pos[id(p)]] = g["weight_decay"]
+            return
+        if sd["next_m"].numel() != self.flat_m.numel() or sd["next_v"].numel() != self.flat_v.numel():
+            raise ValueError("FlatBertAdam.load_state_dict: flat moment buffers of %d elements expected, got %d"
+                             % (self.flat_m.numel(), sd["next_m"].numel()))
         self.step_count.fill_(int(sd["step"]))
         self.flat_m.copy_(sd["next_m"])
         self.flat_v.copy_(sd["next_v"])

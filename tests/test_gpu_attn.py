@@ -75,3 +75,74 @@ def test_attn_probs_fused_dropout_statistics_and_determinism():
     # independence across rows / columns: keep rates per row and per column stay binomial
     assert float((kept.float().mean(-1) - 0.8).abs().max()) < 0.08
     assert float((kept.float().mean(-2) - 0.8).abs().max()) < 0.12
+
+
+def _sq_inputs(B, M, U1, U2, d, Fd, seed=0, bq=None):
+    torch.manual_seed(seed)
+    bq = B if bq is None else bq
+    dev = "cuda"
+    q = _tf32(torch.randn(bq, U1, M * d, device=dev)).requires_grad_()
+    k = _tf32(torch.randn(B, U2, M * d, device=dev)).requires_grad_()
+    vp = _tf32(torch.randn(B, U2, M * Fd, device=dev) * 0.5).requires_grad_()
+    bm = (torch.randn(Fd, device=dev) * 0.1).requires_grad_()
+    Wo = torch.nn.Parameter(torch.randn(M * Fd, Fd, 1, device=dev) * 0.05)
+    bo = torch.nn.Parameter(torch.randn(M * Fd, device=dev) * 0.1)
+    gY = torch.randn(B, M, U1, Fd, device=dev)
+    return q, k, vp, bm, Wo, bo, gY
+
+
+def _unfused(q, k, vp, M, att_p, s1, bm, hid_p, s2, Wo, bo):
+    from segtran_b200 import ops
+    amax = torch.full((1,), -3.0e38, device=q.device)
+    s = ops.attn_scores(q, k, M, amax)
+    P = ops.softmax(s, amax, 500.0, att_p, s1, None)
+    return ops.attn_pv_gelu_group_linear(P, vp, M, bm, hid_p, s2, Wo, bo)
+
+
+@pytest.mark.parametrize("B,bq,M,U1,U2,d,Fd,att_p,hid_p", [
+    (2, 2, 4, 300, 256, 32, 64, 0.0, 0.0),
+    (2, 1, 4, 520, 1024, 64, 128, 0.0, 0.0),          # two-pass scores, shared queries (dq reduced over the batch)
+    (2, 2, 2, 260, 300, 32, 64, 0.2, 0.2),            # both dropouts: masks regenerated in the fused backward
+])
+def test_squeeze_out_fused_matches_unfused_path(B, bq, M, U1, U2, d, Fd, att_p, hid_p):
+    """Same seeds -> same dropout masks: the fused node (sx_attn + softmax-backward GEMM epilogue) must reproduce the
+    separate-kernel path (attn_scores -> sx_softmax -> P.V GEMM -> sx_softmax_bwd) in outputs and all gradients."""
+    from segtran_b200 import ops
+    outs = []
+    for fused in (True, False):
+        q, k, vp, bm, Wo, bo, gY = _sq_inputs(B, M, U1, U2, d, Fd, seed=5, bq=bq)
+        diag = torch.tensor([-3.0e38, 0.0, 0.0], device="cuda")
+        if fused:
+            Y = ops.squeeze_out_fused(q, k, vp, M, 500.0, att_p, 1111, bm, hid_p, 2222, Wo, bo, diag)
+        else:
+            Y = _unfused(q, k, vp, M, att_p, 1111, bm, hid_p, 2222, Wo, bo)
+        (Y * gY).sum().backward()
+        outs.append([Y.detach()] + [t.grad.detach() for t in (q, k, vp, bm, Wo, bo)])
+    names = ["Y", "dq", "dk", "dvp", "dbm", "dWo", "dbo"]
+    for n, a, b in zip(names, outs[0], outs[1]):
+        err = float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+        print(n, "fused vs unfused rel %.2e" % err)
+        assert err < (2e-3 if n in ("dq", "dk") else 5e-4), (n, err)
+
+
+def test_squeeze_out_fused_gradients_match_fp64_autograd():
+    from segtran_b200 import ops
+    B, M, U1, U2, d, Fd = 2, 2, 200, 320, 32, 64
+    q, k, vp, bm, Wo, bo, gY = _sq_inputs(B, M, U1, U2, d, Fd, seed=9)
+    diag = torch.tensor([-3.0e38, 0.0, 0.0], device="cuda")
+    Y = ops.squeeze_out_fused(q, k, vp, M, 500.0, 0.0, 0, bm, 0.0, 0, Wo, bo, diag)
+    (Y * gY).sum().backward()
+    got = [Y.detach()] + [t.grad.detach().clone() for t in (q, k, vp, bm, Wo, bo)]
+    # fp64 autograd of the same math
+    qd, kd, vd, bd, Wd, od = [t.detach().double().requires_grad_() for t in (q, k, vp, bm, Wo, bo)]
+    s = (qd.view(B, U1, M, d).permute(0, 2, 1, 3) @ kd.view(B, U2, M, d).permute(0, 2, 3, 1)) / math.sqrt(d)
+    P = torch.softmax(s, -1)
+    U = P @ vd.view(B, U2, M, Fd).permute(0, 2, 1, 3)
+    G = torch.nn.functional.gelu(U + bd)
+    Yr = torch.einsum("bmnf,mof->bmno", G, Wd.view(M, Fd, Fd)) + od.view(1, M, 1, Fd)
+    (Yr * gY.double()).sum().backward()
+    ref = [Yr.detach()] + [t.grad for t in (qd, kd, vd, bd, Wd, od)]
+    for n, a, b in zip(["Y", "dq", "dk", "dvp", "dbm", "dWo", "dbo"], got, ref):
+        err = float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+        print(n, "rel %.2e" % err)
+        assert err < 3e-3, (n, err)             # TF32 operands (10-bit mantissa) in every contraction

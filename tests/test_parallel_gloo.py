@@ -23,12 +23,21 @@ def _worker(rank, world, port, q, overlap=0):
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.GELU(), torch.nn.Linear(5, 3))
     net[2].weight = net[2].weight                      # plain module; tying handled by id() de-duplication
-    bucket = GradBucket(net.parameters(), overlap_chunks=overlap)
+    milestones = overlap == "milestones"
+    bucket = GradBucket(net.parameters(), overlap_chunks=0 if milestones else overlap, milestones=milestones)
     x = torch.arange(4 * 6, dtype=torch.float32).view(4, 6) / 10.0
     xs = x[rank * 2:(rank + 1) * 2]                    # batch-split data parallelism (train3d.py:495)
+    sent_early = []
     for it in range(2):                                # second iteration checks that .grad views stay attached
         bucket.zero()
-        (net(xs).pow(2).sum() / 2).backward()
+        if milestones:                                 # layer-boundary milestone: backward past h => net[2]'s grads final
+            from segtran_b200 import ops
+            h = net[1](net[0](xs))
+            ops.grad_ready(h, net[2].parameters())
+            (net[2](h).pow(2).sum() / 2).backward()
+            sent_early.append(sum(bucket._sent) == 2 and len(bucket._works) == 1)   # weight+bias merged into one call
+        else:
+            (net(xs).pow(2).sum() / 2).backward()
         bucket.allreduce_async()
         bucket.wait()
     # the bucket pads every parameter to a 256-byte boundary: compare the parameter views, and the padding must stay zero
@@ -40,7 +49,7 @@ def _worker(rank, world, port, q, overlap=0):
     (ref(x).pow(2).sum() / 2 / world).backward()
     want = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
     ok = pad_ok and torch.allclose(flat, want, rtol=1e-5, atol=1e-6) and all(
-        p.grad.data_ptr() >= bucket.flat.data_ptr() for p in net.parameters())
+        p.grad.data_ptr() >= bucket.flat.data_ptr() for p in net.parameters()) and all(sent_early)
     q.put((rank, bool(ok), float((flat - want).abs().max())))
     dist.destroy_process_group()
 
@@ -48,7 +57,7 @@ def _worker(rank, world, port, q, overlap=0):
 import pytest
 
 
-@pytest.mark.parametrize("overlap", [0, 3])
+@pytest.mark.parametrize("overlap", [0, 3, "milestones"])
 def test_grad_bucket_two_ranks_gloo(overlap):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
