@@ -112,7 +112,9 @@ int sx_gemm(const sx_gemm_args* args, void* stream);
  *     P[b][m] = dropout( softmax_keys( min(alpha * Q[b,:,m] K[b,:,m]^T, clip) ) )
  * One persistent tcgen05 kernel replaces segtran_shared.py:566-567 (Q.K^T / sqrt(d)), :569-580 (max statistics and
  * conditional clamp), :601 (softmax) and :605 (attention dropout): the scores stay in TMEM, the softmax runs on the
- * tcgen05.ld fragments, only P is written (plus the raw scaled scores S when the backward needs them).
+ * tcgen05.ld fragments, only P is written (plus the raw scaled scores S when the backward needs them).  More than 256
+ * keys do not fit one TMEM accumulator per row block: the scores are then produced twice (statistics launch, then
+ * probabilities launch, both over (row block, key chunk) tiles) instead of being written and re-read.
  * Q [Bq][U1][M*d] (q_bstride = 0: one query bank shared by the batch), K [B][U2][M*d]; mode m uses columns
  * [m*d, (m+1)*d).  P, S: [B][M][U1][ldp] fp32, ldp % 4 == 0.  lse, rowmax: [B][M][U1] (natural-log units; rowmax is
  * the max of the raw row).  stat: device scratch of two 32-bit words, ZERO-initialised by the caller: [0] the running
@@ -140,6 +142,8 @@ typedef struct {
   uint32_t _pad;
   uint64_t drop_seed;
   const uint64_t* drop_seed_dev;
+  float* scratch;                /* U2 > 256 only: B*M*ceil(U1/256)*ceil(U2/256)*1536 floats of partial row statistics */
+  int64_t scratch_floats;
 } sx_attn_probs_args;
 int sx_attn_probs_fwd(const sx_attn_probs_args* args, void* stream);
 
@@ -213,6 +217,14 @@ int sx_gelu_bwd(const float* dG, const void* H, int32_t h_dtype, int64_t n, floa
                 int32_t dh_dtype, int32_t round_tf32, void* stream);
 /* dtype conversion / TF32 rounding of a flat buffer (weights once per step) */
 int sx_convert(const void* x, int32_t x_dtype, int64_t n, void* y, int32_t y_dtype, int32_t round_tf32, void* stream);
+/* hi = TF32(x), lo = TF32(x - hi) over a flat fp32 buffer: operand split of the 3-pass error-compensated TF32 products
+ * (A_hi B_hi + A_lo B_hi + A_hi B_lo) used by the precision policy for the small / sensitive contractions */
+int sx_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream);
+/* x [Z1][Z0][R][K] with element strides (sz1, sz0, sr, sk) -> out [Z1][Z0][R][3*Kp] contiguous, rows = [hi|lo|hi] (role 0,
+ * the "A" operand) or [hi|hi|lo] (role 1, the "B" operand), segments zero-padded to Kp (multiple of 4) columns: ONE
+ * sx_gemm launch over K' = 3*Kp on the two outputs is the 3-pass product A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T */
+int sx_split_tf32_cat(const float* x, int32_t Z1, int32_t Z0, int32_t R, int32_t K, int64_t sz1, int64_t sz0, int64_t sr,
+                      int64_t sk, int32_t Kp, int32_t role, float* out, void* stream);
 /* out[c] += sum_r X[r,c]   (bias gradients) */
 int sx_colsum(const void* X, int32_t x_dtype, int64_t R, int32_t C, int64_t ld, float* out, void* stream);
 /* out[0] += sum_i x[i]*y[i]  and  y = alpha * (*alpha_dev) * x : a linear loss head for benchmarks / checksums */

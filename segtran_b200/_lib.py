@@ -46,7 +46,8 @@ class sx_attn_probs_args(C.Structure):
                 ("K", C.c_void_p), ("k_ld", C.c_int64), ("k_bstride", C.c_int64), ("alpha", C.c_float),
                 ("clip", C.c_float), ("P", C.c_void_p), ("S", C.c_void_p), ("ldp", C.c_int64), ("lse", C.c_void_p),
                 ("rowmax", C.c_void_p), ("stat", C.c_void_p), ("diag", C.c_void_p), ("drop_p", C.c_float),
-                ("_pad", C.c_uint32), ("drop_seed", C.c_uint64), ("drop_seed_dev", C.c_void_p)]
+                ("_pad", C.c_uint32), ("drop_seed", C.c_uint64), ("drop_seed_dev", C.c_void_p),
+                ("scratch", C.c_void_p), ("scratch_floats", C.c_int64)]
 
 
 _P, _I, _L, _F, _U64, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_double
@@ -71,6 +72,8 @@ _PROTOS = {
     "sx_seed_derive": [_P, _U64, _P, _P],
     "sx_seed_advance": [_P, _U64, _P],
     "sx_convert": [_P, _I, _L, _P, _I, _I, _P],
+    "sx_split_tf32": [_P, _L, _P, _P, _P],
+    "sx_split_tf32_cat": [_P, _I, _I, _I, _I, _L, _L, _L, _L, _I, _I, _P, _P],
     "sx_colsum": [_P, _I, _L, _I, _L, _P, _P],
     "sx_transpose": [_P, _L, _I, _I, _P, _P],
     "sx_colsum_batched": [_P, _I, _L, _I, _L, _L, _I, _L, _P, _P],
@@ -125,7 +128,7 @@ def check(rc, what):
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
 _LAUNCHES = {"sx_pos_lsinu_bwd": 2, "sx_ln_softaggr_bwd": 2, "sx_prologue_bwd": 3, "sx_layernorm_bwd": 2, "sx_gemm_debug_set": 0,
-             "sx_attn_probs_fwd": 2}
+             "sx_attn_probs_fwd": 3}
 launch_count = 0
 _hook = None          # optional callable(name, args) -> context manager, installed by bench.py for per-kernel timing
 

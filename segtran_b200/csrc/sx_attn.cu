@@ -27,6 +27,9 @@
 #include "sx_common.cuh"
 #include "sx_tc.cuh"
 
+long long sx_attn_dbg = 0;                  // bring-up: 1 = skip the TMA stores, 2 = skip staging + stores
+long long sx_attn_mode = 1;                 // bring-up knob (sx_gemm_debug_set "attn_mode"): 1 = one launch, 2 = two tile launches
+
 namespace {
 using namespace sxtc;
 
@@ -52,6 +55,12 @@ __device__ __forceinline__ float ordered_val(unsigned int k) {
 struct AttnParams {
   int B, M, U1, U2, d;
   int tiles_m, tiles_n, num_kb, npass, items;
+  int nwork, nsub;                // work items per launch and accumulator tiles per item (see phase)
+  int phase;                      // 0: whole row block in one accumulator (keys <= 256): statistics + probabilities;
+                                  // 3: item = row block, 2 * tiles_n tiles: pass 0 statistics, pass 1 probabilities;
+                                  // 1: statistics of one (row block, key chunk) tile -> partial (max, sum, raw max);
+                                  // 2: probabilities of one tile from the combined partials
+  float* part;                    // phases 1/2: [items][tiles_n][2 halves][3][256 rows] partial row statistics
   int q_bcast;                    // Q has batch 1 (shared by the batch)
   float alpha2, clip2;            // alpha * log2(e), clip * log2(e)
   float alpha, clip;
@@ -59,6 +68,7 @@ struct AttnParams {
   float* rowmax;                  // [B][M][U1]  max of the raw scaled row (may be null)
   float* stat;                    // zero-initialised; [0] ordered_key(max raw scaled score), [1] += rows whose max < -(clip - 104)
   int store_s;
+  int dbg;
   long long ldp;                  // row pitch of P (and S) in elements, multiple of 4
   float drop_p;
   unsigned long long drop_seed;
@@ -125,23 +135,23 @@ sx_attn_probs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (sx::elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int item = cid; item < p.items; item += ncl) {
+        for (int w = cid; w < p.nwork; w += ncl) {
           int b, m, mb;
-          decode(item, b, m, mb);
+          decode(p.nsub == 1 ? w / p.tiles_n : w, b, m, mb);
           const int m0 = mb * 2 * BM + (int)rank * BM;
           const int qb = p.q_bcast ? 0 : b;
-          for (int pass = 0; pass < p.npass; ++pass)
-            for (int nb = 0; nb < p.tiles_n; ++nb) {
-              const int n0 = nb * BN + (int)rank * (BN / 2);
-              for (int kb = 0; kb < p.num_kb; ++kb) {
-                sx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                if (leader) sx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES * 2);
-                uint8_t* sa = smem + stage * STAGE_BYTES;
-                sx::tma_load_4d_pair(sa, &tmQ, &full_bar[stage], kb * 32, m0, m, qb, sx::kEvictLast);
-                sx::tma_load_4d_pair(sa + A_STAGE_BYTES, &tmK, &full_bar[stage], kb * 32, n0, m, b, sx::kEvictLast);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-              }
+          for (int sub = 0; sub < p.nsub; ++sub) {
+            const int nb = p.nsub == 1 ? w % p.tiles_n : sub % p.tiles_n;
+            const int n0 = nb * BN + (int)rank * (BN / 2);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+              sx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (leader) sx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES * 2);
+              uint8_t* sa = smem + stage * STAGE_BYTES;
+              sx::tma_load_4d_pair(sa, &tmQ, &full_bar[stage], kb * 32, m0, m, qb, sx::kEvictLast);
+              sx::tma_load_4d_pair(sa + A_STAGE_BYTES, &tmK, &full_bar[stage], kb * 32, n0, m, b, sx::kEvictLast);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+          }
         }
       }
     } else if (warp == 1 && leader) {
@@ -151,8 +161,8 @@ sx_attn_probs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int item = cid; item < p.items; item += ncl)
-        for (int sub = 0; sub < p.npass * p.tiles_n; ++sub, ++it) {
+      for (int w = cid; w < p.nwork; w += ncl)
+        for (int sub = 0; sub < p.nsub; ++sub, ++it) {
           const int acc = it & 1;
           const uint32_t acc_phase = (it >> 1) & 1;
           sx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -198,6 +208,7 @@ sx_attn_probs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // one 32 x 32 fp32 tile of this warp (thread = row `lane`, f[0..31] = 32 consecutive columns) -> swizzled staging
     // tile -> two 16-row TMA bulk stores (clipped at the tensor edge by the hardware)
     auto stage_store = [&](const CUtensorMap* tm, const float (&f)[32], int col0, int row0, int z0, int z1) {
+      if (p.dbg == 2) return;
       uint8_t* buf = mystg + (sbuf & 1) * 4096;
       if (lane == 0) sx::tma_store_wait_read<1>();         // the group issued two tiles ago has released this buffer
       __syncwarp();
@@ -207,7 +218,7 @@ sx_attn_probs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
       sx::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && p.dbg != 1) {
         sx::tma_store_4d(tm, buf, col0, row0, z0, z1);
         sx::tma_store_4d(tm, buf + 2048, col0, row0 + 16, z0, z1);
         sx::tma_store_commit();
@@ -216,17 +227,19 @@ sx_attn_probs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     };
 
     int item_par = 0;
-    for (int item = cid; item < p.items; item += ncl, item_par ^= 1) {
+    for (int w = cid; w < p.nwork; w += ncl, item_par ^= 1) {
+      const int item = p.nsub == 1 ? w / p.tiles_n : w;
       int b, m, mb;
       decode(item, b, m, mb);
       const int grow = mb * 2 * BM + (int)rank * BM + rloc;      // this thread's query row
       const int wrow0 = mb * 2 * BM + (int)rank * BM + q * 32;   // first row of this warp
       const long long rowflat = ((long long)b * p.M + m) * p.U1 + grow;
       float rm = -3.0e38f, rl = 0.f, rraw = -3.0e38f;            // running max (clamped), sum, raw max — log2 units
-      float inv_l = 0.f;
+      float inv_l = 0.f, rcp_l = 0.f;                           // exponent offset max + log2(sum) of this row; 1/sum
       float* xm = xch + item_par * (2 * 3 * BM);
 
-      // statistics of one TMEM-resident chunk (this thread's 4 fragments)
+      // statistics of one TMEM-resident chunk (this thread's 4 fragments).  Lean form: one max, one FFMA, one EX2 and one
+      // add per score; the clamp only enters through a warp-uniform slow path taken when some row exceeds it
       auto chunk_stats = [&](uint32_t taddr, int nb) {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -235,25 +248,65 @@ sx_attn_probs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           uint32_t v[32];
           sx::tmem_ld32(taddr + (uint32_t)(h * 128 + c * 32), v);
           sx::tmem_ld_wait();
-          float cm = -3.0e38f, craw = -3.0e38f;
-          float s2[32];
+          if (col0 + 32 > p.U2) {                                 // ragged key count: mask the tail columns
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float s = __uint_as_float(v[i]) * p.alpha2;
-            if (col0 + i >= p.U2) s = -3.0e38f;
-            craw = fmaxf(craw, s);
-            s = fminf(s, p.clip2);
-            s2[i] = s;
-            cm = fmaxf(cm, s);
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i >= p.U2) v[i] = 0xFF7FFFFFu;           // -FLT_MAX
           }
-          const float mn = fmaxf(rm, cm);
-          float acc = 0.f;
+          float cm = __uint_as_float(v[0]);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc += sx::ex2_approx(s2[i] - mn);
-          rl = rl * sx::ex2_approx(rm - mn) + acc;
+          for (int i = 1; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]));
+          cm *= p.alpha2;                                         // alpha2 > 0: the max commutes with the scaling
+          rraw = fmaxf(rraw, cm);
+          const float mn = fmaxf(rm, fminf(cm, p.clip2));
+          float acc0 = 0.f, acc1 = 0.f;
+          if (__any_sync(0xffffffffu, cm > p.clip2)) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              acc0 += sx::ex2_approx(fminf(__uint_as_float(v[i]) * p.alpha2, p.clip2) - mn);
+              acc1 += sx::ex2_approx(fminf(__uint_as_float(v[i + 1]) * p.alpha2, p.clip2) - mn);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              acc0 += sx::ex2_approx(fmaf(__uint_as_float(v[i]), p.alpha2, -mn));
+              acc1 += sx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.alpha2, -mn));
+            }
+          }
+          rl = rl * sx::ex2_approx(rm - mn) + (acc0 + acc1);
           rm = mn;
-          rraw = fmaxf(rraw, craw);
         }
+      };
+      // final (max, sum, raw max) of the row -> 1/sum, and once per row: lse / rowmax / global statistics
+      auto publish = [&](bool once) {
+        inv_l = rm + __log2f(rl);                                 // P = 2^(s2 - max - log2(sum)): no per-element multiply
+        rcp_l = 1.f / rl;                                         // (clamped rows keep the two-step form: |max| = 721)
+        if (once && grow < p.U1) {
+          gmax = fmaxf(gmax, rraw);
+          if (h == 0) {
+            p.lse[rowflat] = (rm + __log2f(rl)) * LN2;
+            if (p.rowmax) p.rowmax[rowflat] = rraw * LN2;
+            if (rraw * LN2 < -(p.clip - 104.f)) ++lowrows;
+          }
+        }
+      };
+      // phase 1: this thread's (max, sum, raw max) over its half of one key chunk -> global partials
+      auto store_partial = [&](int nb) {
+        float* pp = p.part + ((((long long)item * p.tiles_n + nb) * 2 + h) * 3) * (2 * BM) + (int)rank * BM + rloc;
+        pp[0] = rm; pp[2 * BM] = rl; pp[4 * BM] = rraw;
+      };
+      // phase 2: combine the partials of every key chunk and half of this thread's row
+      auto load_partials = [&]() {
+        const float* pp = p.part + ((long long)item * p.tiles_n * 2 * 3) * (2 * BM) + (int)rank * BM + rloc;
+        float mx = -3.0e38f, rw = -3.0e38f;
+        for (int j = 0; j < 2 * p.tiles_n; ++j) {
+          mx = fmaxf(mx, pp[(long long)(j * 3) * (2 * BM)]);
+          rw = fmaxf(rw, pp[(long long)(j * 3 + 2) * (2 * BM)]);
+        }
+        float l = 0.f;
+        for (int j = 0; j < 2 * p.tiles_n; ++j)
+          l += pp[(long long)(j * 3 + 1) * (2 * BM)] * sx::ex2_approx(pp[(long long)(j * 3) * (2 * BM)] - mx);
+        rm = mx; rl = l; rraw = rw;
       };
       // both column halves of a row -> the row's final (max, 1/sum); publishes lse / rowmax
       auto finish_stats = [&]() {
@@ -267,15 +320,7 @@ sx_attn_probs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         rl = rl * sx::ex2_approx(rm - mn) + ol * sx::ex2_approx(om - mn);
         rm = mn;
         rraw = fmaxf(rraw, oraw);
-        inv_l = 1.f / rl;
-        if (grow < p.U1) {
-          gmax = fmaxf(gmax, rraw);
-          if (h == 0) {
-            p.lse[rowflat] = (rm + __log2f(rl)) * LN2;
-            if (p.rowmax) p.rowmax[rowflat] = rraw * LN2;
-            if (rraw * LN2 < -(p.clip - 104.f)) ++lowrows;
-          }
-        }
+        publish(true);
       };
       // probabilities of one TMEM-resident chunk -> P (and the raw scores -> S)
       auto chunk_probs = [&](uint32_t taddr, int nb) {
@@ -292,9 +337,14 @@ sx_attn_probs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
             stage_store(&tmS, f, col0, wrow0, m, b);
           }
+          if (__any_sync(0xffffffffu, rraw > p.clip2)) {          // some row of this warp was clamped (rare)
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            f[i] = sx::ex2_approx(fminf(__uint_as_float(v[i]) * p.alpha2, p.clip2) - rm) * inv_l;
+            for (int i = 0; i < 32; ++i)
+              f[i] = sx::ex2_approx(fminf(__uint_as_float(v[i]) * p.alpha2, p.clip2) - rm) * rcp_l;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = sx::ex2_approx(fmaf(__uint_as_float(v[i]), p.alpha2, -inv_l));
+          }
           if (p.drop_p > 0.f) {
             const unsigned long long g0 = (unsigned long long)((rowflat * p.ldp + col0) >> 2);
 #pragma unroll
@@ -319,24 +369,31 @@ sx_attn_probs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (lane == 0) sx::mbar_arrive_leader(&tempty_bar[acc]);
       };
 
-      for (int pass = 0; pass < p.npass; ++pass)
-        for (int nb = 0; nb < p.tiles_n; ++nb, ++it) {
-          const int acc = it & 1;
-          sx::mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
-          sx::tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-          if (p.npass == 1) {                     // the whole row block is resident: statistics, then probabilities
-            chunk_stats(taddr, nb);
-            finish_stats();
-            chunk_probs(taddr, nb);
-          } else if (pass == 0) {
-            chunk_stats(taddr, nb);
-            if (nb == p.tiles_n - 1) finish_stats();
-          } else {
-            chunk_probs(taddr, nb);
-          }
-          release(acc);
+      for (int sub = 0; sub < p.nsub; ++sub, ++it) {
+        const int nb_t = p.nsub == 1 ? w % p.tiles_n : sub % p.tiles_n;
+        const int acc = it & 1;
+        sx::mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+        sx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        if (p.phase == 0) {                       // the whole row block is resident: statistics, then probabilities
+          chunk_stats(taddr, nb_t);
+          finish_stats();
+          chunk_probs(taddr, nb_t);
+        } else if (p.phase == 1) {                // tile phases: partial statistics -> global
+          chunk_stats(taddr, nb_t);
+          store_partial(nb_t);
+        } else if (p.phase == 2) {                // tile phases: probabilities from the combined partials
+          load_partials();
+          publish(nb_t == 0);
+          chunk_probs(taddr, nb_t);
+        } else if (sub < p.tiles_n) {             // phase 3, row-block items: pass 0 keeps the running statistics ...
+          chunk_stats(taddr, nb_t);
+          if (sub == p.tiles_n - 1) finish_stats();
+        } else {                                  // ... pass 1 recomputes each chunk and emits the probabilities
+          chunk_probs(taddr, nb_t);
         }
+        release(acc);
+      }
     }
     gmax = sx::warp_max(gmax);
     if (lane == 0 && gmax > -3.0e38f) atomicMax(reinterpret_cast<unsigned int*>(&p.stat[0]), ordered_key(gmax * LN2));
@@ -387,6 +444,8 @@ extern "C" int sx_attn_probs_fwd(const sx_attn_probs_args* a, void* stream) {
   p.tiles_n = sx_ceil_div(a->U2, BN);
   p.num_kb = sx_ceil_div(a->d, 32);
   p.npass = p.tiles_n == 1 ? 1 : 2;
+  const long long part_floats = p.tiles_n == 1 ? 0 : (long long)a->B * a->M * p.tiles_m * p.tiles_n * 2 * 3 * (2 * BM);
+  p.part = a->scratch;
   const long long items = (long long)a->B * a->M * p.tiles_m;
   SX_REQUIRE(items < (1ll << 30), "sx_attn_probs_fwd: too many row blocks");
   p.items = (int)items;
@@ -395,6 +454,7 @@ extern "C" int sx_attn_probs_fwd(const sx_attn_probs_args* a, void* stream) {
   p.alpha2 = a->alpha * LOG2E; p.clip2 = a->clip * LOG2E;
   p.lse = a->lse; p.rowmax = a->rowmax; p.stat = a->stat;
   p.store_s = a->S != nullptr;
+  p.dbg = (int)sx_attn_dbg;
   p.ldp = a->ldp;
   p.drop_p = a->drop_p; p.drop_seed = a->drop_seed;
   p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(a->drop_seed_dev);
@@ -422,9 +482,11 @@ extern "C" int sx_attn_probs_fwd(const sx_attn_probs_args* a, void* stream) {
   }
 
   SX_CHECK_CUDA(set_max_smem_once(sx_attn_probs_kernel, SMEM_BYTES));
-  const int pairs = p.items < sms / 2 ? p.items : sms / 2;
+  // keys <= 256: one launch (phase 0).  Otherwise either ONE launch whose work items are whole row blocks (phase 3: both
+  // passes of a block on the same CTA pair, statistics stay in registers) or TWO launches over (row block, key chunk)
+  // tiles (phases 1, 2: finer load balance, partial statistics through global memory); knob "attn_mode" (1 / 2 launches)
+  const bool two = p.tiles_n > 1 && sx_attn_mode == 2 && a->scratch && a->scratch_floats >= part_floats;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = reinterpret_cast<cudaStream_t>(stream);
@@ -435,7 +497,14 @@ extern "C" int sx_attn_probs_fwd(const sx_attn_probs_args* a, void* stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sx_attn_probs_kernel, tq, tk, tp, ts, p));
+  for (int ph = (p.tiles_n == 1 ? 0 : (two ? 1 : 3)); ph <= (p.tiles_n == 1 ? 0 : (two ? 2 : 3)); ++ph) {
+    p.phase = ph;
+    p.nsub = ph == 3 ? 2 * p.tiles_n : 1;
+    p.nwork = ph == 3 ? p.items : p.items * p.tiles_n;
+    const int pairs = p.nwork < sms / 2 ? p.nwork : sms / 2;
+    cfg.gridDim = dim3(2 * pairs);
+    SX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sx_attn_probs_kernel, tq, tk, tp, ts, p));
+  }
   SX_CHECK_CUDA(cudaGetLastError());
   if (a->diag) {
     attn_diag_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a->stat, a->clip, a->diag);

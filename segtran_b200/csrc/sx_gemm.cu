@@ -20,6 +20,8 @@
 #include "sx_common.cuh"
 #include "sx_tc.cuh"
 
+extern long long sx_attn_mode, sx_attn_dbg;  // csrc/sx_attn.cu
+
 namespace {
 using namespace sxtc;
 
@@ -647,6 +649,8 @@ extern "C" int sx_gemm_debug_set(const char* key, int64_t value) {
   else if (k == "stream_out") g_knobs.stream_out = value;
   else if (k == "cg2") g_knobs.cg2 = value;
   else if (k == "c_tma") g_knobs.c_tma = value;
+  else if (k == "attn_mode") sx_attn_mode = value;
+  else if (k == "attn_dbg") sx_attn_dbg = value;
   else {
     sx_set_error("sx_gemm_debug_set: unknown key %s", key);
     return -1;

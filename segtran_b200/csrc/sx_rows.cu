@@ -544,6 +544,41 @@ __global__ void convert_kernel(const TI* __restrict__ x, long long n, TO* __rest
     stf<TO>(y + i, ldf<TI>(x + i), rnd);
 }
 
+// hi = TF32(x), lo = TF32(x - hi): the operand split of the error-compensated 3-pass TF32 products
+__global__ void split_tf32_kernel(const float* __restrict__ x, long long n, float* __restrict__ hi, float* __restrict__ lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float h = sx::round_tf32(v);
+    hi[i] = h;
+    lo[i] = sx::round_tf32(v - h);
+  }
+}
+
+// x[z1][z0][r][k] (arbitrary element strides) -> out[z1][z0][r][3*Kp] = [hi | lo | hi] (role 0) or [hi | hi | lo] (role 1),
+// hi = TF32(x), lo = TF32(x - hi), each segment zero-padded to Kp columns: the K-concatenated operands of a ONE-launch
+// error-compensated product  A'.B'^T = A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T
+__global__ void split_cat_kernel(const float* __restrict__ x, int Z0, int R, int K, long long sz1, long long sz0,
+                                 long long sr, long long sk, int Kp, int role, float* __restrict__ out) {
+  const long long row = blockIdx.x;                      // (z1, z0, r) flattened
+  const int r = (int)(row % R);
+  const long long z = row / R;
+  const int z0 = (int)(z % Z0);
+  const long long z1 = z / Z0;
+  const float* xr = x + z1 * sz1 + z0 * sz0 + (long long)r * sr;
+  float* o = out + row * 3ll * Kp;
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    float h = 0.f, l = 0.f;
+    if (k < K) {
+      const float v = xr[(long long)k * sk];
+      h = sx::round_tf32(v);
+      l = sx::round_tf32(v - h);
+    }
+    o[k] = h;
+    o[Kp + k] = role == 0 ? l : h;
+    o[2 * Kp + k] = role == 0 ? h : l;
+  }
+}
+
 // out[c] += sum_r X[r, c]   (bias gradients).  blockDim (32, 8)
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ X, long long R, int C, long long ld, float* __restrict__ out) {
@@ -1057,6 +1092,25 @@ extern "C" int sx_convert(const void* x, int32_t x_dtype, int64_t n, void* y, in
     convert_kernel<__nv_bfloat16, float><<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)x, n, (float*)y, 0);
   else
     SX_REQUIRE(false, "sx_convert: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split_tf32_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(x, n, hi, lo);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_split_tf32_cat(const float* x, int32_t Z1, int32_t Z0, int32_t R, int32_t K, int64_t sz1, int64_t sz0,
+                                 int64_t sr, int64_t sk, int32_t Kp, int32_t role, float* out, void* stream) {
+  SX_REQUIRE(Z1 > 0 && Z0 > 0 && R > 0 && K > 0 && Kp >= K && Kp % 4 == 0, "sx_split_tf32_cat: bad shape");
+  const long long rows = (long long)Z1 * Z0 * R;
+  SX_REQUIRE(rows < (1ll << 31), "sx_split_tf32_cat: too many rows");
+  split_cat_kernel<<<(unsigned)rows, Kp >= 256 ? 256 : 64, 0, ST(stream)>>>(x, Z0, R, K, sz1, sz0, sr, sk, Kp, role, out);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -367,8 +367,11 @@ class CrossAttFeatTrans(nn.Module):
         if in_key is None:
             in_key = in_query
         M = self.num_modes
-        q = ops.linear(in_query, self.query.weight, self.query.bias)
-        k = ops.linear(in_key, self.key.weight, self.key.bias)
+        # precision classes: a projection of at most num_attractors rows is "small", a token-row projection "proj"
+        tq = "small" if in_query.shape[1] <= self.config.num_attractors else "proj"
+        tk = "small" if in_key.shape[1] <= self.config.num_attractors else "proj"
+        q = ops.linear(in_query, self.query.weight, self.query.bias, tag=tq)
+        k = ops.linear(in_key, self.key.weight, self.key.bias, tag=tk)
         dev = q.device
         if self._diag is None or self._diag.device != dev:
             self._diag = torch.tensor([-3.0e38, 0.0, 0.0], device=dev)
@@ -429,8 +432,9 @@ class SqueezedAttFeatTrans(nn.Module):
         so the [N x C x C] key and value GEMMs become [A x C x C] ones; exact up to fp rounding."""
         t = self.in_ator_trans
         C = self.in_feat_dim
-        q1 = ops.linear(self.attractors, t.query.weight, t.query.bias)               # [1,A,C]
-        qw = ops.linear(q1, t.key.weight.t())                                         # Q1 Wk            [1,A,C]
+        x3 = ops.rt_for("small") == 0         # the attractor-row chain runs as 3-pass products: keep q1 unrounded for it
+        q1 = ops.linear(self.attractors, t.query.weight, t.query.bias, tag="small", round_out=not x3)   # [1,A,C]
+        qw = ops.linear(q1, t.key.weight.t(), tag="small")                            # Q1 Wk            [1,A,C]
         rb = None
         if t.key.bias is not None:                                                    # (Q1 . bk) / sqrt(C)  [A]
             rb = ops.scale(ops.matvec(q1[0], t.key.bias), 1.0 / math.sqrt(C))
@@ -438,16 +442,18 @@ class SqueezedAttFeatTrans(nn.Module):
         if t._diag is None or t._diag.device != dev:
             t._diag = torch.tensor([-3.0e38, 0.0, 0.0], device=dev)
         amax = torch.full((1,), -3.0e38, device=dev)
-        s = ops.attn_scores(qw, in_feat, 1, amax, rb)                                  # [B,1,A,N]
+        s = ops.attn_scores(qw, in_feat, 1, amax, rb, tag="insq")                      # [B,1,A,N]
         p = t.att_dropout.p if t.training else 0.0
         probs = ops.softmax(s, amax, float(t.attn_clip), p, ops.new_dropout_seed(dev) if p > 0 else 0, t._diag)
         t.attention_scores = s if t.keep_attn_scores else None
         if t.training:
             t.call_count += 1
-        u = ops.attn_pv(probs, in_feat, 1)                                             # P1 h            [B,1,A,C]
+        u = ops.attn_pv(probs, in_feat, 1, tag="insq", round_out=not x3)               # P1 h            [B,1,A,C]
         ot = t.out_trans
-        z = ops.linear(u[:, 0], ot.first_linear.weight)                                # (P1 h) Wv^T     [B,A,C]
-        return ops.layer_norm(z, ot.first_norm_layer.weight, ot.first_norm_layer.bias)
+        z = ops.linear(u[:, 0], ot.first_linear.weight, tag="small", round_out=False)  # (P1 h) Wv^T     [B,A,C]
+        # the updated attractors feed the squeeze-out key projection and the value bank: both "small"
+        return ops.layer_norm(z, ot.first_norm_layer.weight, ot.first_norm_layer.bias, consumer_tag="small",
+                              producer_tag="small")
 
     def forward(self, in_feat, pos_biases=None):
         if pos_biases is not None:

@@ -37,6 +37,39 @@ def get_precision() -> str:
     return _PRECISION
 
 
+# Per-contraction precision policy of the default ("tf32") mode.  Every GEMM call site carries a tag:
+#   "small": attractor-row and weight-space products (A rows or none: q1, Q1.Wk, the in-squeeze value projection, the
+#            squeeze-out key projection, the folded value bank W' = Wm Wv and V' = a W'^T) — a few % of the FLOPs;
+#   "proj" : token-row projections (N rows x C x C: the squeeze-out query projection);
+#   "insq" : the in-squeeze attention products (A x N x C);
+#   "big"  : scores, P.V', the grouped output Linear and everything in backward that is their size.
+# A tag mapped to "tf32x3" runs as three TF32 passes on hi/lo operand splits (fp32-grade products); "tf32" is one
+# pass on TF32-rounded operands.  The default keeps the small contractions exact — they feed every token through the
+# attractor bank, so their rounding error is shared by all outputs — at no measurable cost; set_precision_policy(
+# proj="tf32x3") buys another ~30 % error reduction at the wide 2-D configs for ~1.3x their step time.
+_POLICY = {"small": "tf32x3", "proj": "tf32", "insq": "tf32", "big": "tf32"}
+
+
+def set_precision_policy(**kw):
+    for k, v in kw.items():
+        if k not in _POLICY or v not in ("tf32", "tf32x3"):
+            raise ValueError("set_precision_policy: unknown tag/mode %s=%r" % (k, v))
+        _POLICY[k] = v
+
+
+def get_precision_policy():
+    return dict(_POLICY)
+
+
+def _three_pass(tag: str) -> bool:
+    return _PRECISION == "tf32x3" or (_PRECISION == "tf32" and _POLICY.get(tag, "tf32") == "tf32x3")
+
+
+def rt_for(tag: str) -> int:
+    """round-to-TF32 flag for a producer whose output is consumed ONLY by contractions of class `tag`."""
+    return 0 if _three_pass(tag) else 1
+
+
 # Direct gradient accumulation (opt-in, used by parallel.GradBucket(direct_accumulate=True)): when a weight is a leaf
 # whose .grad already exists (a view into the flat gradient bucket), the weight-gradient GEMM / bias column sum
 # accumulates straight into it and autograd receives None for that input — this removes the zero-fill of a temporary
@@ -350,53 +383,39 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
     return out
 
 
-def _tf32_split(t: torch.Tensor):
-    """fp32 view -> (hi, lo) with the same strides: hi = TF32(t), lo = TF32(t - hi)   (tf32x3 validation mode)."""
-    if any(st == 0 and sz > 1 for st, sz in zip(t.stride(), t.shape)):
-        t = t.contiguous()
-    hi = torch.empty_strided(t.size(), t.stride(), device=t.device, dtype=torch.float32)
-    hi.copy_(t)
-    hi.view(torch.int32).add_(0x1000).bitwise_and_(-8192)
-    lo = torch.empty_strided(t.size(), t.stride(), device=t.device, dtype=torch.float32)
-    torch.sub(t, hi, out=lo)
-    lo.view(torch.int32).add_(0x1000).bitwise_and_(-8192)
-    return hi, lo
-
-
 def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = None, alpha: float = 1.0,
             bias: Optional[torch.Tensor] = None, bias_mode: int = L.SX_BIAS_N, gelu: bool = False,
             preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
             amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
             reduce_z1: bool = False, gelu_bwd: Optional[torch.Tensor] = None,
             addend: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
-            rowdot=None, softmax_bwd=None) -> torch.Tensor:
-    """C[..., m, n] = epilogue(alpha * sum_k a[..., m, k] b[..., n, k]) on the tcgen05 GEMM.  In the default
-    precision this is one launch; in 'tf32x3' it is three passes on the hi/lo operand splits."""
-    if _PRECISION == "tf32":
+            rowdot=None, softmax_bwd=None, tag: str = "big") -> torch.Tensor:
+    """C[..., m, n] = epilogue(alpha * sum_k a[..., m, k] b[..., n, k]) on the tcgen05 GEMM.  One launch on TF32-rounded
+    operands, or — in 'tf32x3' mode / for call-site classes the precision policy maps to it — three passes on the hi/lo
+    operand splits (fp32-grade products)."""
+    if not _three_pass(tag):
         return _gemm_nt_1(a, b, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
                           accumulate=accumulate, split_k=split_k, amax=amax, drop_p=drop_p, seed=seed,
                           round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd, addend=addend, colsum=colsum,
                           rowdot=rowdot, softmax_bwd=softmax_bwd)
     _req_cuda(a, b)
-    ah, al = _tf32_split(a)
-    bh, bl = _tf32_split(b)
-    if accumulate or reduce_z1:              # linear epilogue: the three passes simply accumulate into C
-        out = _gemm_nt_1(al, bh, out=out, alpha=alpha, accumulate=accumulate, reduce_z1=reduce_z1, split_k=1,
-                         round_out=False)
-        _gemm_nt_1(ah, bl, out=out, alpha=alpha, accumulate=True, reduce_z1=reduce_z1, split_k=1, round_out=False)
-        return _gemm_nt_1(ah, bh, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, accumulate=True,
-                          reduce_z1=reduce_z1, split_k=1, round_out=False)
-    a4, b4 = _as4(a), _as4(b)
-    if out is None:
-        out = torch.empty((max(a4.shape[0], b4.shape[0]), max(a4.shape[1], b4.shape[1]), a4.shape[-2], b4.shape[-2]),
-                          device=a.device, dtype=torch.float32)
-    o4 = _as4(out)
-    part = torch.empty_strided(o4.size(), o4.stride(), device=a.device, dtype=torch.float32)    # C's layout
-    _gemm_nt_1(al, bh, out=part, alpha=alpha, split_k=1, round_out=False, addend=addend)
-    _gemm_nt_1(ah, bl, out=part, alpha=alpha, split_k=1, round_out=False, addend=part)
-    return _gemm_nt_1(ah, bh, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
-                      split_k=1, amax=amax, drop_p=drop_p, seed=seed, round_out=False, addend=part, gelu_bwd=gelu_bwd,
-                      colsum=colsum, rowdot=rowdot, softmax_bwd=softmax_bwd)
+    # ONE launch over K-concatenated operand splits: [A_hi | A_lo | A_hi] . [B_hi | B_hi | B_lo]^T (fp32 accumulation in TMEM
+    # over the three partial products), so every epilogue / accumulate / split-K option works unchanged
+    return _gemm_nt_1(_split_cat(a, 0), _split_cat(b, 1), out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu,
+                      preact=preact, accumulate=accumulate, split_k=split_k, amax=amax, drop_p=drop_p, seed=seed,
+                      round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd, addend=addend, colsum=colsum,
+                      rowdot=rowdot, softmax_bwd=softmax_bwd)
+
+
+def _split_cat(t: torch.Tensor, role: int) -> torch.Tensor:
+    """[..., R, K] fp32 view (any strides) -> contiguous [z1, z0, R, 3*pad4(K)] K-concatenated TF32 split (see sx_split_tf32_cat)."""
+    t4 = _as4(t)
+    Z1, Z0, R, K = t4.shape
+    Kp = _pad4(K)
+    out = torch.empty((Z1, Z0, R, 3 * Kp), device=t.device, dtype=torch.float32)
+    L.call("sx_split_tf32_cat", t4.data_ptr(), Z1, Z0, R, K, t4.stride(0), t4.stride(1), t4.stride(2), t4.stride(3), Kp, role,
+           out.data_ptr(), _stream())
+    return out
 
 
 def _pad4(n: int) -> int:
@@ -460,55 +479,57 @@ def colsum(x2d: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tenso
 # autograd functions
 # ------------------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
-    """y = dropout(act(x W^T + b)).  nn.Linear call sites segtran_shared.py:243, :414, :559-560."""
+    """y = dropout(act(x W^T + b)).  nn.Linear call sites segtran_shared.py:243, :414, :559-560.  `tag` = precision class
+    of the three products (forward, dx, dW), see the precision policy above."""
 
     @staticmethod
-    def forward(ctx, x, W, b, gelu, drop_p, seed):
+    def forward(ctx, x, W, b, gelu, drop_p, seed, tag, round_y):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        Wr = round_tf32(W)
+        Wr = W.contiguous() if _three_pass(tag) else round_tf32(W)
         O = W.shape[0]
         y = torch.empty((x2.shape[0], O), device=x.device, dtype=torch.float32)
         h = torch.empty_like(y) if gelu else None
-        gemm_nt(x2, Wr, out=y, bias=b, gelu=gelu, preact=h, drop_p=drop_p, seed=seed)
+        gemm_nt(x2, Wr, out=y, bias=b, gelu=gelu, preact=h, drop_p=drop_p, seed=seed, tag=tag, round_out=round_y)
         ctx.save_for_backward(x2, Wr, h)
-        ctx.meta = (shp, b is not None, gelu, drop_p, seed)
+        ctx.meta = (shp, b is not None, gelu, drop_p, seed, tag)
         ctx.leaves = (W, b)
         return y.view(*shp[:-1], O)
 
     @staticmethod
     def backward(ctx, dy):
         x2, Wr, h = ctx.saved_tensors
-        shp, has_b, gelu, drop_p, seed = ctx.meta
+        shp, has_b, gelu, drop_p, seed, tag = ctx.meta
         dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
         if gelu:
             dh = torch.empty_like(dy2)
             L.call("sx_gelu_bwd", dy2.data_ptr(), h.data_ptr(), L.SX_F32, dy2.numel(), drop_p, *_seed_args(seed), dh.data_ptr(),
-                   L.SX_F32, _rt(), _stream())
+                   L.SX_F32, rt_for(tag), _stream())
             dy2 = dh
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
-            dx = gemm_nt(dy2, Wr.t(), round_out=False).view(shp)
+            dx = gemm_nt(dy2, Wr.t(), round_out=False, tag=tag).view(shp)
         W, b = ctx.leaves
         if ctx.needs_input_grad[1]:
             tgt = _grad_target(W)
             if tgt is not None:
-                gemm_nt(dy2.t(), x2.t(), out=tgt, accumulate=True, round_out=False)
+                gemm_nt(dy2.t(), x2.t(), out=tgt, accumulate=True, round_out=False, tag=tag)
             else:
-                dW = gemm_nt(dy2.t(), x2.t(), round_out=False).view(Wr.shape)
+                dW = gemm_nt(dy2.t(), x2.t(), round_out=False, tag=tag).view(Wr.shape)
         if has_b and ctx.needs_input_grad[2]:
             tgt = _grad_target(b)
             if tgt is not None:
                 colsum(dy2, out=tgt)
             else:
                 db = colsum(dy2)
-        return dx, dW, db, None, None, None
+        return dx, dW, db, None, None, None, None, None
 
 
-def linear(x, W, b=None, gelu=False, drop_p=0.0, seed=0):
-    return _Linear.apply(x, W, b, gelu, drop_p, seed)
+def linear(x, W, b=None, gelu=False, drop_p=0.0, seed=0, tag="big", round_out=True):
+    """round_out: round y to TF32 (set False when every consumer of y is a 3-pass contraction or not a GEMM)."""
+    return _Linear.apply(x, W, b, gelu, drop_p, seed, tag, round_out)
 
 
 class _AttnScores(torch.autograd.Function):
@@ -518,7 +539,7 @@ class _AttnScores(torch.autograd.Function):
     SqueezedAttFeatTrans): it is added after the scaling, so it must already be scaled."""
 
     @staticmethod
-    def forward(ctx, q, k, M, amax, row_bias):
+    def forward(ctx, q, k, M, amax, row_bias, tag):
         Bq, U1, Cq = q.shape
         B, U2 = k.shape[0], k.shape[1]
         d = Cq // M
@@ -529,9 +550,10 @@ class _AttnScores(torch.autograd.Function):
         if row_bias is not None and M != 1:
             raise L.SxError("attn_scores: row_bias needs a single mode")
         rb = row_bias.contiguous().view(-1) if row_bias is not None else None
-        gemm_nt(qv, kv, out=S, alpha=scale, amax=amax, round_out=False, bias=rb, bias_mode=L.SX_BIAS_M)
+        gemm_nt(qv, kv, out=S, alpha=scale, amax=amax, round_out=False, bias=rb, bias_mode=L.SX_BIAS_M, tag=tag)
         ctx.save_for_backward(q, k)
         ctx.meta = (M, d, scale, row_bias.shape if row_bias is not None else None)
+        ctx.tag = tag
         return S
 
     @staticmethod
@@ -547,16 +569,16 @@ class _AttnScores(torch.autograd.Function):
             bcast = Bq == 1 and B > 1
             dq = _zeros_like(q) if bcast else torch.empty_like(q)
             gemm_nt(dS, k.view(B, U2, M, d).permute(0, 2, 3, 1), out=dq.view(Bq, U1, M, d).permute(0, 2, 1, 3),
-                    alpha=scale, round_out=False, reduce_z1=bcast, split_k=1)
+                    alpha=scale, round_out=False, reduce_z1=bcast, split_k=1, tag=ctx.tag)
         if ctx.needs_input_grad[1]:
             dk = torch.empty_like(k)
             gemm_nt(dS.transpose(-1, -2), q.view(Bq, U1, M, d).permute(0, 2, 3, 1),
-                    out=dk.view(B, U2, M, d).permute(0, 2, 1, 3), alpha=scale, round_out=False)
+                    out=dk.view(B, U2, M, d).permute(0, 2, 1, 3), alpha=scale, round_out=False, tag=ctx.tag)
         if rb_shape is not None and ctx.needs_input_grad[4]:
             drb = _zeros((U1,), q.device)     # sum over batch and keys
             L.call("sx_rowsum", dS.data_ptr(), B * U1, U2, dS.stride(-2), U1, drb.data_ptr(), _stream())
             drb = drb.view(rb_shape)
-        return dq, dk, None, None, drb
+        return dq, dk, None, None, drb, None
 
 
 def attn_probs_fused(q, k, M, clip=500.0, drop_p=0.0, seed=0, diag=None, need_scores=False, round_out=True):
@@ -588,6 +610,10 @@ def attn_probs_fused(q, k, M, clip=500.0, drop_p=0.0, seed=0, diag=None, need_sc
     a.lse, a.rowmax, a.stat, a.diag = lse.data_ptr(), rowmax.data_ptr(), stat.data_ptr(), _ptr(diag)
     a.drop_p = drop_p
     a.drop_seed, a.drop_seed_dev = _seed_args(seed)
+    if U2 > 256:                              # partial row statistics of the (row block, key chunk) tiles
+        nfl = B * M * ((U1 + 255) // 256) * ((U2 + 255) // 256) * 1536
+        scratch = torch.empty(nfl, device=q.device, dtype=torch.float32)
+        a.scratch, a.scratch_floats = scratch.data_ptr(), nfl
     L.call("sx_attn_probs_fwd", C.byref(a), _stream())
     return P, S, lse, rowmax, stat
 
@@ -690,15 +716,16 @@ class _AttnPV(torch.autograd.Function):
     """U[b,m] = P[b,m] V[b,:,m]   with V [B,U2,M*F], channel = m*F+f  (segtran_shared.py:414-419, :447)."""
 
     @staticmethod
-    def forward(ctx, P, v, M):
+    def forward(ctx, P, v, M, tag, round_out):
         B, _, U1, U2 = P.shape
         Fd = v.shape[-1] // M
         vv = v.view(B, U2, M, Fd).permute(0, 2, 3, 1)          # [B,M,F,U2]: the "N x K" operand, F contiguous
         P = _rowpad(P)
         U = torch.empty((B, M, U1, Fd), device=P.device, dtype=torch.float32)
-        gemm_nt(P, vv, out=U)
+        gemm_nt(P, vv, out=U, tag=tag, round_out=round_out)
         ctx.save_for_backward(P, v)
         ctx.meta = (M, Fd)
+        ctx.tag = tag
         return U
 
     @staticmethod
@@ -711,13 +738,13 @@ class _AttnPV(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # dP[b,m] (U1 x U2) = dU[b,m] (U1 x F) . V[b,m]^T  -> operand "B" = V[b,m] as [U2, F]
             dP = _rowpad_empty((B, M, U1, U2), P.device)
-            gemm_nt(dU, v.view(B, U2, M, Fd).permute(0, 2, 1, 3), out=dP, round_out=False)
+            gemm_nt(dU, v.view(B, U2, M, Fd).permute(0, 2, 1, 3), out=dP, round_out=False, tag=ctx.tag)
         if ctx.needs_input_grad[1]:
             dv = torch.empty_like(v)
             # dV[b,m] (U2 x F) = P[b,m]^T (U2 x U1) . dU[b,m] (U1 x F)
             gemm_nt(P.transpose(-1, -2), dU.transpose(-1, -2), out=dv.view(B, U2, M, Fd).permute(0, 2, 1, 3),
-                    round_out=False)
-        return dP, dv, None
+                    round_out=False, tag=ctx.tag)
+        return dP, dv, None, None, None
 
 
 class _AttnPVGelu(torch.autograd.Function):
@@ -773,10 +800,12 @@ class _FoldedValueBank(torch.autograd.Function):
         a2 = a.reshape(B * A, Cd)
         if not a2.is_contiguous():
             a2 = a2.contiguous()
-        Wvr = round_tf32(Wv).view(M, 1, Fd, Cd)                       # [m, f, c]
-        Wmr = round_tf32(Wm)                                          # [o, f]
-        Wf = gemm_nt(Wmr.view(1, 1, Fd, Fd), Wvr.transpose(-1, -2))   # [M,1,F(o),C] = Wm Wv_m, TF32-rounded
-        Vp = gemm_nt(a2, Wf.view(M * Fd, Cd))[0, 0]                   # [B*A, M*F]
+        x3 = _three_pass("small")
+        Wvr = (Wv.contiguous() if x3 else round_tf32(Wv)).view(M, 1, Fd, Cd)      # [m, f, c]
+        Wmr = Wm.contiguous() if x3 else round_tf32(Wm)                           # [o, f]
+        # W'_m = Wm Wv_m [M,1,F(o),C]: kept unrounded when the bank projection below runs as a 3-pass product
+        Wf = gemm_nt(Wmr.view(1, 1, Fd, Fd), Wvr.transpose(-1, -2), tag="small", round_out=not x3)
+        Vp = gemm_nt(a2, Wf.view(M * Fd, Cd), tag="small")[0, 0]      # [B*A, M*F], TF32-rounded: the P.V' operand
         ctx.save_for_backward(a2, Wf, Wvr, Wmr)
         ctx.meta = (B, A, Cd, Fd, M, Wv.shape)
         ctx.leaves = (Wv, Wm)
@@ -792,22 +821,22 @@ class _FoldedValueBank(torch.autograd.Function):
             d2 = d2.contiguous()
         da = dWv = dWm = None
         if ctx.needs_input_grad[0]:
-            da = gemm_nt(d2, Wf.view(M * Fd, Cd).t(), round_out=False)[0, 0].view(B, A, Cd)
+            da = gemm_nt(d2, Wf.view(M * Fd, Cd).t(), round_out=False, tag="small")[0, 0].view(B, A, Cd)
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            dWf = gemm_nt(d2.t(), a2.t(), round_out=False).view(M, 1, Fd, Cd)          # [m, o, c]
+            dWf = gemm_nt(d2.t(), a2.t(), round_out=False, tag="small").view(M, 1, Fd, Cd)          # [m, o, c]
             if ctx.needs_input_grad[2]:                               # dWm[o,f] = sum_m dW'_m[o,:] . Wv_m[f,:]
                 tgt = _grad_target(Wm)
                 if tgt is not None:
-                    gemm_nt(dWf, Wvr, out=tgt.view(1, 1, Fd, Fd), reduce_z1=True, accumulate=True, round_out=False)
+                    gemm_nt(dWf, Wvr, out=tgt.view(1, 1, Fd, Fd), reduce_z1=True, accumulate=True, round_out=False, tag="small")
                 else:
-                    dWm = gemm_nt(dWf, Wvr, reduce_z1=True, round_out=False).view(Fd, Fd)
+                    dWm = gemm_nt(dWf, Wvr, reduce_z1=True, round_out=False, tag="small").view(Fd, Fd)
             if ctx.needs_input_grad[1]:                               # dWv_m[f,c] = sum_o Wm[o,f] dW'_m[o,c]
                 tgt = _grad_target(Wv)
                 if tgt is not None:
                     gemm_nt(Wmr.t().view(1, 1, Fd, Fd), dWf.transpose(-1, -2), out=tgt.view(M, 1, Fd, Cd), accumulate=True,
-                            round_out=False)
+                            round_out=False, tag="small")
                 else:
-                    dWv = gemm_nt(Wmr.t().view(1, 1, Fd, Fd), dWf.transpose(-1, -2), round_out=False).view(wv_shape)
+                    dWv = gemm_nt(Wmr.t().view(1, 1, Fd, Fd), dWf.transpose(-1, -2), round_out=False, tag="small").view(wv_shape)
         return da, dWv, dWm, None
 
 
@@ -996,13 +1025,14 @@ class _LayerNorm(torch.autograd.Function):
     """nn.LayerNorm(C, eps=1e-12, affine) over the last dim (first_norm_layer, segtran_shared.py:456)."""
 
     @staticmethod
-    def forward(ctx, x, g, b):
+    def forward(ctx, x, g, b, rnd, rnd_bwd):
+        ctx.rnd_bwd = rnd_bwd
         x = x.contiguous()
         Cd = x.shape[-1]
         R = x.numel() // Cd
         y = torch.empty_like(x)
         stats = torch.empty((R, 2), device=x.device, dtype=torch.float32)
-        L.call("sx_layernorm_fwd", x.data_ptr(), R, Cd, g.data_ptr(), b.data_ptr(), y.data_ptr(), L.SX_F32, _rt(),
+        L.call("sx_layernorm_fwd", x.data_ptr(), R, Cd, g.data_ptr(), b.data_ptr(), y.data_ptr(), L.SX_F32, rnd,
                stats.data_ptr(), _stream())
         ctx.save_for_backward(x, g, stats)
         ctx.leaves = (g, b)
@@ -1018,8 +1048,8 @@ class _LayerNorm(torch.autograd.Function):
         dgb, dg = _sink_or_zeros(ctx.leaves[0])
         dbb, db = _sink_or_zeros(ctx.leaves[1])
         L.call("sx_layernorm_bwd", dy.data_ptr(), x.data_ptr(), R, Cd, g.data_ptr(), stats.data_ptr(), dx.data_ptr(),
-               L.SX_F32, _rt(), dgb.data_ptr(), dbb.data_ptr(), _stream())
-        return dx, dg, db
+               L.SX_F32, ctx.rnd_bwd, dgb.data_ptr(), dbb.data_ptr(), _stream())
+        return dx, dg, db, None, None
 
 
 class _GroupLinear(torch.autograd.Function):
@@ -1207,8 +1237,8 @@ def dot(x, w):
     return _Dot.apply(x, w.contiguous())
 
 
-def attn_scores(q, k, M, amax=None, row_bias=None):
-    return _AttnScores.apply(q, k, M, amax, row_bias)
+def attn_scores(q, k, M, amax=None, row_bias=None, tag="big"):
+    return _AttnScores.apply(q, k, M, amax, row_bias, tag)
 
 
 def softmax(S, amax=None, clip=500.0, drop_p=0.0, seed=0, diag=None):
@@ -1216,12 +1246,15 @@ def softmax(S, amax=None, clip=500.0, drop_p=0.0, seed=0, diag=None):
     return _Softmax.apply(S, amax, clip, drop_p, seed, diag)
 
 
-def attn_pv(P, v, M):
-    return _AttnPV.apply(P, v, M)
+def attn_pv(P, v, M, tag="big", round_out=True):
+    return _AttnPV.apply(P, v, M, tag, round_out)
 
 
-def layer_norm(x, g, b):
-    return _LayerNorm.apply(x, g, b)
+def layer_norm(x, g, b, consumer_tag=None, producer_tag=None):
+    """consumer_tag / producer_tag: precision class of the contractions that consume y / that produced x (they decide
+    whether y, respectively dx, is TF32-rounded here)."""
+    return _LayerNorm.apply(x, g, b, _rt() if consumer_tag is None else rt_for(consumer_tag),
+                            _rt() if producer_tag is None else rt_for(producer_tag))
 
 
 def group_linear(G, Wo, bo):

@@ -21,11 +21,12 @@ def tf32(x):
 
 EXACT = set()
 COUNT = {}
+LAYER = [0]
 
 
 def _site(name):
     COUNT[name] = COUNT.get(name, 0) + 1
-    return name in EXACT
+    return name in EXACT or ("L%d:*" % LAYER[0]) in EXACT or ("L%d:%s" % (LAYER[0], name)) in EXACT
 
 
 class Patched:
@@ -63,6 +64,13 @@ def run(dims, A, grid, qkb, seed, emulate):
     pos = O.voxels_pos_for_grid(grid, (8, 8), 2)
     mask = (torch.rand(2, N, 1) > 0.1).float()
     P = Patched()
+    sq = O.squeezed_layer
+
+    def sq_layer(p_, pre, *a, **k):
+        LAYER[0] = int(pre.rstrip(".").split(".")[-1])
+        return sq(p_, pre, *a, **k)
+
+    O.squeezed_layer = sq_layer
     with torch.no_grad():
         ref = O.fusion_encoder(p, "voxel_fusion.", x, pos, mask, dims, 4)
         out = {}
@@ -82,7 +90,12 @@ if __name__ == "__main__":
     cfgs = [([1792, 1792, 896, 448], 256, (36, 36), False), ([2048, 2048, 2048], 256, (22, 22), True)]
     for dims, A, grid, qkb in cfgs:
         for seed in range(5, 5 + int(sys.argv[1]) if len(sys.argv) > 1 else 8):
-            variants = {"all_tf32": set(), "einsum_exact": {"einsum"}, "matmul_exact": {"matmul"}}
+            L = len(dims) - 1
+            variants = {"all_tf32": set(), "einsum_exact": {"einsum"}, "last_layer_exact": {"L%d:*" % (L - 1)},
+                        "first_layer_exact": {"L0:*"}, "last_einsum_exact": {"L%d:einsum" % (L - 1)},
+                        "all_linear_exact": {k for k in ("linear%dx%d" % (a, b) for a in (448, 896, 1792, 2048, 3584, 7168, 8192)
+                                                                     for b in (448, 896, 1792, 2048))},
+                        "einsum+matmul_exact": {"einsum", "matmul"}}
             o, c = run(dims, A, grid, qkb, seed, variants)
             print(dims, "seed", seed, {k: "%.2e" % v for k, v in o.items()}, flush=True)
         print(c)
