@@ -38,12 +38,7 @@ enum { SX_OP_TF32 = 0, SX_OP_BF16 = 1 };
 enum { SX_MAJOR_K = 0, SX_MAJOR_MN = 1 };
 enum { SX_BIAS_NONE = 0, SX_BIAS_N = 1, SX_BIAS_M = 2 };
 enum { SX_ACT_NONE = 0, SX_ACT_GELU = 1,
-       SX_ACT_GELU_BWD = 2 /* C = dropmask * (alpha A.B^T) * gelu'(preact): `preact` is an INPUT in C's layout */,
-       SX_ACT_SOFTMAX_BWD = 3 /* C = dS = P * (dropmask * (alpha A.B^T) - row_dot[m]), zero where the score was clamped:
-                                 the softmax backward (segtran_shared.py:601-605) in the epilogue of the dP = dU V^T product.
-                                 P = exp(min(S, clip) - row_lse[m]) is recomputed from the raw scaled scores S given through
-                                 `preact` (C's layout); drop_* describe the ATTENTION dropout of the forward (index = flat
-                                 index in C's layout, the layout of P) */ };
+       SX_ACT_GELU_BWD = 2 /* C = dropmask * (alpha A.B^T) * gelu'(preact): `preact` is an INPUT in C's layout */ };
 
 int sx_version(void);
 const char* sx_last_error(void);
@@ -95,14 +90,6 @@ typedef struct {
                                     error-compensated 3-pass TF32 mode (A_hi B_hi + A_lo B_hi + A_hi B_lo) */
   float* colsum;                 /* optional [N] fp32: += column sums of the stored values over all rows and batch slices
                                     (a bias gradient that would otherwise need its own pass over the output) */
-  float* rowdot;                 /* SX_ACT_GELU_BWD only, optional [Z1][Z0][M] fp32 (contiguous): += sum_n C[m][n] *
-                                    (preact[m][n] - rowdot_sub[n]) — with C = dU and preact - bias = U = P.V this is the
-                                    softmax backward's row term sum_a P_a dP_a = sum_f dU_f U_f, obtained without a pass over P */
-  const float* rowdot_sub;       /* [N] fp32 or NULL (= zeros) */
-  const float* row_lse;          /* SX_ACT_SOFTMAX_BWD: [Z1][Z0][M] log-sum-exp of the clamped score rows */
-  const float* row_dot;          /* SX_ACT_SOFTMAX_BWD: [Z1][Z0][M] the row term produced through `rowdot` */
-  float clip;                    /* SX_ACT_SOFTMAX_BWD: attention clamp (scores above it were clamped: zero gradient) */
-  int32_t _pad4;
 } sx_gemm_args;
 
 int sx_gemm(const sx_gemm_args* args, void* stream);
@@ -117,9 +104,9 @@ int sx_gemm(const sx_gemm_args* args, void* stream);
  * probabilities launch, both over (row block, key chunk) tiles) instead of being written and re-read.
  * Q [Bq][U1][M*d] (q_bstride = 0: one query bank shared by the batch), K [B][U2][M*d]; mode m uses columns
  * [m*d, (m+1)*d).  P, S: [B][M][U1][ldp] fp32, ldp % 4 == 0.  lse, rowmax: [B][M][U1] (natural-log units; rowmax is
- * the max of the raw row).  stat: device scratch of two 32-bit words, ZERO-initialised by the caller: [0] the running
+ * the max of the raw row).  stat: device scratch of three 32-bit words, ZERO-initialised by the caller: [0] the running
  * maximum of the scores under an order-preserving float->uint map (0 = none yet), [1] (float) number of rows whose
- * maximum is below -(clip - 104).  diag (optional, device float[3]): [0] running
+ * maximum is below -(clip - 104), [2] (written at the end) the maximum as a plain float — the `amax` of sx_softmax_bwd.  diag (optional, device float[3]): [0] running
  * max, [1] += 1 when the clamp fired (max > clip), [2] += stat[1] in that case (rows where the reference's LOWER
  * clamp could have mattered — the upper clamp is applied exactly; see sx_attn.cu).
  * ------------------------------------------------------------------------------------------- */
@@ -212,6 +199,13 @@ int sx_ln_softaggr_bwd(const float* dout, const float* Y, int32_t B, int32_t M, 
                        const float* wts, void* dY, int32_t dy_dtype, int32_t round_tf32, float* dg, float* db,
                        float* dws, float* dbs, float* dscore_scratch /* [B*M*N] or NULL */, void* stream);
 
+/* LearnedSoftAggregate on its own (segtran_shared.py:318-325; the no-FFN branch :453 with M modes — the Polyformer layer):
+ *   w = softmax_modes(x_m . ws + bs);  out = sum_m w_m x_m.   x [B,M,N,F] -> out [B,N,F], wts [B,M,N].
+ * backward: dx [B,M,N,F] and dscore [B,M,N] (d ws = sum dscore x, d bs = sum dscore are left to the caller). */
+int sx_softaggr_fwd(const float* x, int32_t B, int32_t M, int32_t N, int32_t F, const float* ws, const float* bs, float* out,
+                    float* wts, void* stream);
+int sx_softaggr_bwd(const float* dout, const float* x, int32_t B, int32_t M, int32_t N, int32_t F, const float* ws,
+                    const float* wts, float* dx, float* dscore, void* stream);
 /* dH = dropout'(dG) * gelu'(H)  (MMSharedMid backward, segtran_shared.py:243-245) */
 int sx_gelu_bwd(const float* dG, const void* H, int32_t h_dtype, int64_t n, float drop_p, uint64_t seed, const uint64_t* seed_dev, void* dH,
                 int32_t dh_dtype, int32_t round_tf32, void* stream);
@@ -220,8 +214,8 @@ int sx_convert(const void* x, int32_t x_dtype, int64_t n, void* y, int32_t y_dty
 /* hi = TF32(x), lo = TF32(x - hi) over a flat fp32 buffer: operand split of the 3-pass error-compensated TF32 products
  * (A_hi B_hi + A_lo B_hi + A_hi B_lo) used by the precision policy for the small / sensitive contractions */
 int sx_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream);
-/* x [Z1][Z0][R][K] with element strides (sz1, sz0, sr, sk) -> out [Z1][Z0][R][3*Kp] contiguous, rows = [hi|lo|hi] (role 0,
- * the "A" operand) or [hi|hi|lo] (role 1, the "B" operand), segments zero-padded to Kp (multiple of 4) columns: ONE
+/* x [Z1][Z0][R][K] with element strides (sz1, sz0, sr, sk) -> out [Z1][Z0][R][3*Kp] contiguous, rows = [lo|hi|hi] (role 0,
+ * the "A" operand) or [hi|lo|hi] (role 1, the "B" operand), segments zero-padded to Kp (multiple of 4) columns: ONE
  * sx_gemm launch over K' = 3*Kp on the two outputs is the 3-pass product A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T */
 int sx_split_tf32_cat(const float* x, int32_t Z1, int32_t Z0, int32_t R, int32_t K, int64_t sz1, int64_t sz0, int64_t sr,
                       int64_t sk, int32_t Kp, int32_t role, float* out, void* stream);
@@ -306,6 +300,17 @@ int sx_resize_axis_bwd(const float* dy, int64_t outer, int32_t Lin, int32_t Lout
 int sx_sgemm_small(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int64_t sam, int64_t sak,
                    int64_t sbk, int64_t sbn, int64_t scm, int64_t scn, int32_t Z, int64_t saz, int64_t sbz, int64_t scz,
                    float alpha, int32_t accumulate, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Sliding-window inference post-process (code/test_util3d.py:93-184):
+ * sx_sw_accumulate: preds[k][window] += sigmoid(scores[k]), cnt[window] += 1 for one patch ([K][dx][dy][dz] scores, window
+ *   origin (x0,y0,z0) in the [K][H][W][D] accumulators)                                              (test_util3d.py:155-159)
+ * sx_sw_finalize: preds /= cnt; brats: make_brats_pred_consistent(is_conservative=False) (datasets3d.py:53-59), hard[1:] =
+ *   preds >= 0.5, hard[0] = no class fired (hard is [K][V]); otherwise hard[0..V) = argmax_k as a float class index.
+ * ------------------------------------------------------------------------------------------- */
+int sx_sw_accumulate(const float* scores, int32_t K, int32_t dx, int32_t dy, int32_t dz, float* preds, float* cnt,
+                     int32_t H, int32_t W, int32_t D, int32_t x0, int32_t y0, int32_t z0, void* stream);
+int sx_sw_finalize(float* preds, const float* cnt, int32_t K, int64_t V, int32_t brats, float* hard, void* stream);
 
 /* debug knobs for bring-up (descriptor field overrides); not part of the stable ABI */
 int sx_gemm_debug_set(const char* key, int64_t value);

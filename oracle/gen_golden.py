@@ -218,11 +218,81 @@ def gen_train():
     print("train_bertadam_tiny: 4 steps, |p0| after", float(after[-1][0].abs().max()))
 
 
+def gen_poly(name="poly2d_tiny", seed=31):
+    """Reference Polyformer layer (code/networks/polyformer.py): output and gradients on a small feature map."""
+    R.load()
+    import networks.polyformer as ref_poly                      # /root/reference/code/networks/polyformer.py
+    args = Namespace(num_attractors=8, num_modes=4, tie_qk_scheme="loose", qk_have_bias=True, pos_code_type="lsinu")
+    torch.manual_seed(seed)
+    with R.quiet():
+        net = ref_poly.Polyformer(32, chan_axis=1, args=args)
+    net.eval()
+    torch.manual_seed(seed + 1)
+    x = torch.randn(2, 32, 12, 10).requires_grad_()
+    G = torch.randn(2, 32, 12, 10)
+    with R.quiet():
+        y = net(x)
+    gp, gi = _grads(net, (y * G).sum(), [x])
+    torch.save(dict(kind="poly", args=vars(args), feat_dim=32, x=x.detach(), G=G, out=y.detach(),
+                    state_dict={k: v.clone() for k, v in net.state_dict().items()}, grad_params=gp, grad_x=gi[0]),
+               os.path.join(OUT, name + ".pt"))
+    print(name, "out", tuple(y.shape), "max|out|", float(y.abs().max()))
+
+
+def gen_infer():
+    """Sliding-window inference fixtures produced by the reference's own test_util3d.test_single_case (un-padded volumes:
+    the reference's padding branch hands F.pad the pads in the wrong dimension order, test_util3d.py:119-120, and cannot run)."""
+    import types
+    R.load()
+    for name in ("h5py", "nibabel", "medpy", "medpy.metric", "common_util", "tqdm"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            sys.modules[name] = m
+    sys.modules["medpy"].metric = sys.modules["medpy.metric"]
+    sys.modules["common_util"].get_filename = lambda p: p
+    sys.modules["tqdm"].tqdm = lambda x, **k: x
+    import test_util3d as T3                                    # /root/reference/code/test_util3d.py
+    from tests.helpers import AffinePickNet
+    zeros = torch.zeros
+
+    def zeros_cpu(*a, **kw):
+        if kw.get("device") == "cuda":
+            kw["device"] = "cpu"
+        return zeros(*a, **kw)
+
+    cases = {}
+    specs = [("brats_same", "brats", 4, (4, 40, 36, 30), (24, 24, 16), (24, 24, 16), 3, 12, 8),
+             ("brats_resized", "brats", 4, (4, 33, 41, 27), (24, 20, 16), (16, 16, 12), 4, 10, 8),
+             ("argmax", "other", 3, (2, 30, 30, 20), (16, 16, 12), (16, 16, 12), 5, 8, 6)]
+    for key, task, K, shp, ops_, ips, bs, sxy, szz in specs:
+        torch.manual_seed(len(key))
+        image = torch.randn(*shp) * 2.0
+        a = [1.0 + 0.5 * k for k in range(K)]
+        b = [-0.3 + 0.2 * k for k in range(K)]
+        ch = [k % shp[0] for k in range(K)]
+        net = AffinePickNet(a, b, ch)
+        torch.zeros = zeros_cpu
+        try:
+            hard, soft = T3.test_single_case(net, image, ops_, ips, bs, sxy, szz, task, "segtran", K)
+        finally:
+            torch.zeros = zeros
+        cases[key] = dict(task=task, K=K, image=image, orig_patch=ops_, input_patch=ips, batch_size=bs, stride_xy=sxy,
+                          stride_z=szz, a=a, b=b, ch=ch, hard=hard, soft=soft)
+        print("infer", key, tuple(hard.shape), tuple(soft.shape), float(soft.mean()))
+    torch.save(dict(kind="infer", cases=cases), os.path.join(OUT, "infer_sw.pt"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
     if len(sys.argv) > 1 and sys.argv[1] == "train":
         gen_train()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "infer":
+        gen_infer()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "poly":
+        gen_poly()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         gen_encoder("enc2d_nosqueeze", [64, 64], 4, 8, 2, True, (6, 7), 2, seed=21, squeeze=False)
@@ -235,6 +305,8 @@ def main():
     gen_encoder("enc3d_ragged", [96, 96], 4, 24, 3, True, (5, 3, 7), 3, seed=9)       # N=105: not a tile multiple
     gen_seg3d("seg3d_tiny")
     gen_seg2d("seg2d_tiny")
+    gen_infer()
+    gen_poly()
 
 
 if __name__ == "__main__":

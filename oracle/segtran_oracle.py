@@ -278,6 +278,23 @@ def hot_path_2d(p: Params, feat_fpn: Tensor, curr_feat: Tensor, vmask: Tensor, o
     return seg_head_2d(p, curr_feat, fused, grid, out_size)
 
 
+def polyformer_layer(p: Params, pre: str, in_feat: Tensor, num_modes: int = 4, **kw) -> Tensor:
+    """PolyformerLayer.forward (code/networks/polyformer.py:35-60, chan_axis = 1, poly_do_layernorm False):
+    2x2 average pooling (:39), channels swapped with the LAST dim and flattened to tokens (:41, :46), attractors attend
+    to the tokens and the tokens to the updated attractors — both CrossAttFeatTrans WITHOUT the FFN, M modes soft-aggregated
+    (segtran_shared.py:452-457) — then back to the map layout, bilinear up-sampling (:56-57) and the residual (:58)."""
+    B, C = in_feat.shape[:2]
+    half0 = F.avg_pool2d(in_feat, 2)
+    half = half0.transpose(1, -1)
+    vfeat = half.reshape(B, -1, C)
+    att = p[pre + "attractors"].expand(B, -1, -1)
+    a = cross_att(p, pre + "in_ator_trans.", att, vfeat, num_modes, C, False, **kw)
+    out = cross_att(p, pre + "ator_out_trans.", vfeat, a, num_modes, C, False, **kw)
+    out = out.transpose(1, -1).reshape(half0.shape)
+    up = F.interpolate(out, size=in_feat.shape[2:], mode="bilinear", align_corners=False)
+    return in_feat + up
+
+
 def dice_hard(a: Tensor, b: Tensor) -> float:
     """2|A∩B| / (|A|+|B|) on boolean masks (test_util2d.py:229-237 restated; 1.0 when both empty)."""
     a = a.bool()

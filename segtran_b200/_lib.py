@@ -15,7 +15,7 @@ SX_F32, SX_BF16 = 0, 1
 SX_OP_TF32, SX_OP_BF16 = 0, 1
 SX_MAJOR_K, SX_MAJOR_MN = 0, 1
 SX_BIAS_NONE, SX_BIAS_N, SX_BIAS_M = 0, 1, 2
-SX_ACT_NONE, SX_ACT_GELU, SX_ACT_GELU_BWD, SX_ACT_SOFTMAX_BWD = 0, 1, 2, 3
+SX_ACT_NONE, SX_ACT_GELU, SX_ACT_GELU_BWD = 0, 1, 2
 SX_SCHED_WARMUP_LINEAR, SX_SCHED_WARMUP_CONSTANT = 0, 1
 
 
@@ -35,9 +35,7 @@ class sx_gemm_args(C.Structure):
                 ("alpha", C.c_float), ("bias_mode", C.c_int32), ("bias", C.c_void_p), ("bias_stride_z0", C.c_int64),
                 ("bias_stride_z1", C.c_int64), ("act", C.c_int32), ("accumulate", C.c_int32), ("preact", C.c_void_p),
                 ("split_k", C.c_int32), ("_pad2", C.c_int32), ("amax", C.c_void_p), ("drop_p", C.c_float),
-                ("_pad3", C.c_uint32), ("drop_seed", C.c_uint64), ("drop_seed_dev", C.c_void_p), ("addend", C.c_void_p), ("colsum", C.c_void_p),
-                ("rowdot", C.c_void_p), ("rowdot_sub", C.c_void_p), ("row_lse", C.c_void_p), ("row_dot", C.c_void_p),
-                ("clip", C.c_float), ("_pad4", C.c_int32)]
+                ("_pad3", C.c_uint32), ("drop_seed", C.c_uint64), ("drop_seed_dev", C.c_void_p), ("addend", C.c_void_p), ("colsum", C.c_void_p)]
 
 
 class sx_attn_probs_args(C.Structure):
@@ -68,10 +66,14 @@ _PROTOS = {
     "sx_layernorm_bwd": [_P, _P, _L, _I, _P, _P, _P, _I, _I, _P, _P, _P],
     "sx_ln_softaggr_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _F, _U64, _P, _P, _P, _P, _P],
     "sx_ln_softaggr_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _U64, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P],
+    "sx_softaggr_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "sx_softaggr_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "sx_gelu_bwd": [_P, _P, _I, _L, _F, _U64, _P, _P, _I, _I, _P],
     "sx_seed_derive": [_P, _U64, _P, _P],
     "sx_seed_advance": [_P, _U64, _P],
     "sx_convert": [_P, _I, _L, _P, _I, _I, _P],
+    "sx_sw_accumulate": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "sx_sw_finalize": [_P, _P, _I, _L, _I, _P, _P],
     "sx_split_tf32": [_P, _L, _P, _P, _P],
     "sx_split_tf32_cat": [_P, _I, _I, _I, _I, _L, _L, _L, _L, _I, _I, _P, _P],
     "sx_colsum": [_P, _I, _L, _I, _L, _P, _P],

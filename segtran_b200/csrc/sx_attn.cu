@@ -417,12 +417,15 @@ sx_attn_probs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 // diag[0] = running max of the scores, diag[1] += 1 when the clamp fired, diag[2] += rows the lower clamp could have
 // touched in a clamped call (see the header comment)  — the module's max_attn / clamp_count counters
 // (segtran_shared.py:575-587) without host synchronisation
-__global__ void attn_diag_kernel(const float* stat, float clip, float* diag) {
+__global__ void attn_diag_kernel(float* stat, float clip, float* diag) {
   const float mx = ordered_val(__float_as_uint(stat[0]));
-  diag[0] = fmaxf(diag[0], mx);
-  if (mx > clip) {
-    diag[1] += 1.f;
-    diag[2] += stat[1];
+  stat[2] = mx;                                  // the plain float maximum (what sx_softmax_bwd's `amax` expects)
+  if (diag) {
+    diag[0] = fmaxf(diag[0], mx);
+    if (mx > clip) {
+      diag[1] += 1.f;
+      diag[2] += stat[1];
+    }
   }
 }
 
@@ -506,9 +509,7 @@ extern "C" int sx_attn_probs_fwd(const sx_attn_probs_args* a, void* stream) {
     SX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sx_attn_probs_kernel, tq, tk, tp, ts, p));
   }
   SX_CHECK_CUDA(cudaGetLastError());
-  if (a->diag) {
-    attn_diag_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a->stat, a->clip, a->diag);
-    SX_CHECK_CUDA(cudaGetLastError());
-  }
+  attn_diag_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a->stat, a->clip, a->diag);
+  SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

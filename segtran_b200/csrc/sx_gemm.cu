@@ -53,11 +53,6 @@ struct GemmParams {
   const unsigned long long* drop_seed_dev;
   const float* addend;   // optional fp32 tensor in C's layout added to alpha*acc before bias/activation (tf32x3 passes)
   float* colsum;         // optional [N]: += column sums of the stored values over all rows and batch slices (bias gradients)
-  float* rowdot;         // GELU_BWD: optional [Z1][Z0][M]: += sum_n C[m][n] * (preact[m][n] - rowdot_sub[n])
-  const float* rowdot_sub;
-  const float* row_lse;  // SOFTMAX_BWD: [Z1][Z0][M]
-  const float* row_dot;  // SOFTMAX_BWD: [Z1][Z0][M]
-  float clip;
   // descriptor fields (bring-up knobs; defaults are the canonical encodings)
   unsigned int lbo_k, sbo_k, lbo_mn_a, lbo_mn_b, sbo_mn, desc_version;
   int dbg_epi;      // bring-up: 0 normal, 1 skip global stores, 2 skip TMEM loads too
@@ -369,17 +364,6 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      float rdot[4] = {0.f, 0.f, 0.f, 0.f};             // [P][h] GELU_BWD row dot products of this tile
-      float sm_lse[4] = {0.f, 0.f, 0.f, 0.f}, sm_dot[4] = {0.f, 0.f, 0.f, 0.f};
-      const long long zrow = ((long long)z1 * p.Z0 + z0) * p.M;
-      if (p.act == SX_ACT_SOFTMAX_BWD) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = row0 + 16 * (i >> 1) + 8 * (i & 1) + tr;
-          sm_lse[i] = r < p.M ? p.row_lse[zrow + r] * 1.4426950408889634f : 0.f;
-          sm_dot[i] = r < p.M ? p.row_dot[zrow + r] : 0.f;
-        }
-      }
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         const int col0 = nb * BN + c * 32;
@@ -463,43 +447,6 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           load_frag(reinterpret_cast<const float*>(p.preact), g, zoff, row0, col0);
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] *= sx::gelu_erf_grad(g[i]);
-          if (p.rowdot) {
-            // this thread's share of sum_n dU[m][n] * U[m][n]  (U = h - bias), rows [P][h]
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int col = col0 + 8 * j + tc;
-              const float s0 = (p.rowdot_sub && col < p.N) ? p.rowdot_sub[col] : 0.f;
-              const float s1 = (p.rowdot_sub && col + 1 < p.N) ? p.rowdot_sub[col + 1] : 0.f;
-#pragma unroll
-              for (int P = 0; P < 2; ++P)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const int i0 = 16 * P + 4 * j + 2 * h;
-                  rdot[2 * P + h] += f[i0] * (g[i0] - s0) + f[i0 + 1] * (g[i0 + 1] - s1);
-                }
-            }
-          }
-        } else if (p.act == SX_ACT_SOFTMAX_BWD) {
-          // dS = P * (mask * keep_scale * dPd - D), P = exp(min(s, clip) - lse) recomputed from the raw scores; zero
-          // where the forward clamped the score
-          apply_dropout();
-          float g[32];
-          load_frag(reinterpret_cast<const float*>(p.preact), g, zoff, row0, col0);
-#pragma unroll
-          for (int P = 0; P < 2; ++P)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float l2 = sm_lse[2 * P + h], dd = sm_dot[2 * P + h];
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int i0 = 16 * P + 4 * j + 2 * h + e;
-                  const float sv = g[i0];
-                  const float pv = sx::ex2_approx(fminf(sv, p.clip) * 1.4426950408889634f - l2);
-                  f[i0] = sv > p.clip ? 0.f : pv * (f[i0] - dd);
-                }
-            }
         } else {
           if (p.preact) {
             if (CG2 && p.c_tma) tma_store(&tmP, f, row0, col0, z0, z1);
@@ -564,16 +511,6 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) {
         if constexpr (CG2) sx::mbar_arrive_leader(&tempty_bar[acc]);
         else sx::mbar_arrive(&tempty_bar[acc]);
-      }
-      if (p.rowdot) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float v = rdot[i];
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          const int r = row0 + 16 * (i >> 1) + 8 * (i & 1) + tr;
-          if ((lane & 3) == 0 && r < p.M) atomicAdd(p.rowdot + zrow + r, v);
-        }
       }
     }
     if (p.amax) {
@@ -717,12 +654,6 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
   p.act = a->act; p.accumulate = a->accumulate; p.preact = a->preact; p.amax = a->amax;
   p.addend = a->addend;
   p.colsum = a->colsum;
-  p.rowdot = a->rowdot; p.rowdot_sub = a->rowdot_sub;
-  p.row_lse = a->row_lse; p.row_dot = a->row_dot; p.clip = a->clip;
-  SX_REQUIRE(!a->rowdot || a->act == SX_ACT_GELU_BWD, "sx_gemm: rowdot needs SX_ACT_GELU_BWD");
-  SX_REQUIRE(a->act != SX_ACT_SOFTMAX_BWD || (a->preact && a->row_lse && a->row_dot && a->c_dtype == SX_F32 &&
-                                              !a->accumulate && a->split_k <= 1 && !a->bias),
-             "sx_gemm: SX_ACT_SOFTMAX_BWD needs the scores in `preact`, row_lse, row_dot, fp32 C, no bias, split_k=1");
   SX_REQUIRE(a->act != SX_ACT_GELU_BWD || (a->preact && a->c_dtype == SX_F32 && p.split_k == 1 && !a->accumulate),
              "sx_gemm: SX_ACT_GELU_BWD needs the fp32 pre-activation in `preact`, fp32 C, split_k=1, accumulate=0");
   SX_REQUIRE(!a->addend || (p.split_k == 1 && !a->accumulate && a->c_dtype == SX_F32), "sx_gemm: addend needs split_k=1, accumulate=0, fp32 C");
@@ -756,7 +687,7 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
       (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 && (!a->preact || (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0)) {
     rc = make_out_map(&tc, a->C, a->N, a->M, a->Z0, a->Z1, a->ldc, a->c_stride_z0, a->c_stride_z1);
     if (rc) return rc;
-    if (a->preact && a->act != SX_ACT_GELU_BWD && a->act != SX_ACT_SOFTMAX_BWD) {
+    if (a->preact && a->act != SX_ACT_GELU_BWD) {
       rc = make_out_map(&tp, a->preact, a->N, a->M, a->Z0, a->Z1, a->ldc, a->c_stride_z0, a->c_stride_z1);
       if (rc) return rc;
     }

@@ -544,6 +544,70 @@ __global__ void convert_kernel(const TI* __restrict__ x, long long n, TO* __rest
     stf<TO>(y + i, ldf<TI>(x + i), rnd);
 }
 
+// ------------------------------------------------------------------------------------------------
+// LearnedSoftAggregate on its own (segtran_shared.py:318-325; the no-FFN branch of ExpandedFeatTrans, :453, used by the
+// Polyformer layer with M modes):  w = softmax_m(x_m . ws + bs);  out = sum_m w_m x_m.   x [B,M,N,F] -> out [B,N,F].
+// One warp per token; rows are streamed (no shared memory), M <= MAX_MODES.
+// ------------------------------------------------------------------------------------------------
+__global__ void softaggr_fwd_kernel(const float* __restrict__ x, int B, int M, int N, int F, const float* __restrict__ ws,
+                                    const float* __restrict__ bs, float* __restrict__ out, float* __restrict__ wts) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  for (long long t = (long long)blockIdx.x * warps + warp; t < (long long)B * N; t += (long long)gridDim.x * warps) {
+    const int b = (int)(t / N), n = (int)(t % N);
+    float sc[MAX_MODES];
+    float mx = -3.0e38f;
+    for (int m = 0; m < M; ++m) {
+      const float* xr = x + (((long long)b * M + m) * N + n) * F;
+      float a = 0.f;
+      for (int c = lane; c < F; c += 32) a += xr[c] * ws[c];
+      a = sx::warp_sum(a) + bs[0];
+      sc[m] = a;
+      mx = fmaxf(mx, a);
+    }
+    float den = 0.f;
+    for (int m = 0; m < M; ++m) { sc[m] = __expf(sc[m] - mx); den += sc[m]; }
+    const float inv = 1.f / den;
+    for (int m = 0; m < M; ++m) {
+      sc[m] *= inv;
+      if (lane == 0) wts[((long long)b * M + m) * N + n] = sc[m];
+    }
+    float* o = out + ((long long)b * N + n) * F;
+    for (int c = lane; c < F; c += 32) {
+      float a = 0.f;
+      for (int m = 0; m < M; ++m) a += sc[m] * x[(((long long)b * M + m) * N + n) * F + c];
+      o[c] = a;
+    }
+  }
+}
+
+// dx_m = w_m dout + dscore_m ws,  dscore_m = w_m (<dout, x_m> - sum_k w_k <dout, x_k>);  dscore [B,M,N] is also written
+// out (the caller reduces d ws = sum dscore x and d bs = sum dscore with the library's small-GEMM / row-sum kernels)
+__global__ void softaggr_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, int B, int M, int N, int F,
+                                    const float* __restrict__ ws, const float* __restrict__ wts, float* __restrict__ dx,
+                                    float* __restrict__ dscore) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  for (long long t = (long long)blockIdx.x * warps + warp; t < (long long)B * N; t += (long long)gridDim.x * warps) {
+    const int b = (int)(t / N), n = (int)(t % N);
+    const float* dr = dout + ((long long)b * N + n) * F;
+    float w[MAX_MODES], dw[MAX_MODES];
+    float wd = 0.f;
+    for (int m = 0; m < M; ++m) {
+      const float* xr = x + (((long long)b * M + m) * N + n) * F;
+      float a = 0.f;
+      for (int c = lane; c < F; c += 32) a += dr[c] * xr[c];
+      dw[m] = sx::warp_sum(a);
+      w[m] = wts[((long long)b * M + m) * N + n];
+      wd += w[m] * dw[m];
+    }
+    for (int m = 0; m < M; ++m) {
+      const float ds = w[m] * (dw[m] - wd);
+      if (lane == 0) dscore[((long long)b * M + m) * N + n] = ds;
+      float* o = dx + (((long long)b * M + m) * N + n) * F;
+      for (int c = lane; c < F; c += 32) o[c] = w[m] * dr[c] + ds * ws[c];
+    }
+  }
+}
+
 // hi = TF32(x), lo = TF32(x - hi): the operand split of the error-compensated 3-pass TF32 products
 __global__ void split_tf32_kernel(const float* __restrict__ x, long long n, float* __restrict__ hi, float* __restrict__ lo) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -554,9 +618,9 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, long long n, floa
   }
 }
 
-// x[z1][z0][r][k] (arbitrary element strides) -> out[z1][z0][r][3*Kp] = [hi | lo | hi] (role 0) or [hi | hi | lo] (role 1),
+// x[z1][z0][r][k] (arbitrary element strides) -> out[z1][z0][r][3*Kp] = [lo | hi | hi] (role 0) or [hi | lo | hi] (role 1),
 // hi = TF32(x), lo = TF32(x - hi), each segment zero-padded to Kp columns: the K-concatenated operands of a ONE-launch
-// error-compensated product  A'.B'^T = A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T
+// error-compensated product  A'.B'^T = A_lo B_hi^T + A_hi B_lo^T + A_hi B_hi^T
 __global__ void split_cat_kernel(const float* __restrict__ x, int Z0, int R, int K, long long sz1, long long sz0,
                                  long long sr, long long sk, int Kp, int role, float* __restrict__ out) {
   const long long row = blockIdx.x;                      // (z1, z0, r) flattened
@@ -573,9 +637,11 @@ __global__ void split_cat_kernel(const float* __restrict__ x, int Z0, int R, int
       h = sx::round_tf32(v);
       l = sx::round_tf32(v - h);
     }
-    o[k] = h;
-    o[Kp + k] = role == 0 ? l : h;
-    o[2 * Kp + k] = role == 0 ? h : l;
+    // the two small cross products come FIRST in the reduction order: the tensor core's fp32 accumulator is still small
+    // while they are added, so they are not swallowed by the rounding of the large hi.hi partial sum
+    o[k] = role == 0 ? l : h;
+    o[Kp + k] = role == 0 ? h : l;
+    o[2 * Kp + k] = h;
   }
 }
 
@@ -1092,6 +1158,24 @@ extern "C" int sx_convert(const void* x, int32_t x_dtype, int64_t n, void* y, in
     convert_kernel<__nv_bfloat16, float><<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)x, n, (float*)y, 0);
   else
     SX_REQUIRE(false, "sx_convert: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_softaggr_fwd(const float* x, int32_t B, int32_t M, int32_t N, int32_t F, const float* ws, const float* bs,
+                               float* out, float* wts, void* stream) {
+  SX_REQUIRE(M >= 1 && M <= MAX_MODES && B > 0 && N > 0 && F > 0, "sx_softaggr_fwd: bad shape (modes %d)", M);
+  softaggr_fwd_kernel<<<grid_for_rows((long long)B * N, ROW_WARPS, sms_cached() * 4), ROW_WARPS * 32, 0, ST(stream)>>>(
+      x, B, M, N, F, ws, bs, out, wts);
+  SX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sx_softaggr_bwd(const float* dout, const float* x, int32_t B, int32_t M, int32_t N, int32_t F, const float* ws,
+                               const float* wts, float* dx, float* dscore, void* stream) {
+  SX_REQUIRE(M >= 1 && M <= MAX_MODES && B > 0 && N > 0 && F > 0, "sx_softaggr_bwd: bad shape (modes %d)", M);
+  softaggr_bwd_kernel<<<grid_for_rows((long long)B * N, ROW_WARPS, sms_cached() * 4), ROW_WARPS * 32, 0, ST(stream)>>>(
+      dout, x, B, M, N, F, ws, wts, dx, dscore);
   SX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -178,6 +178,14 @@ class LearnedSoftAggregate(nn.Module):
         self.feat2score = nn.Linear(num_feat, 1)
         self.keepdim = keepdim
 
+    def forward(self, x, score_basis=None):
+        """x [B,M,U,F] -> [B,U,F] (reference :318-325, group_dim = 1).  The fused LayerNorm + aggregate of the FFN branch
+        (ops.ln_softaggr) does not go through here; this is the stand-alone form (no-FFN branch, Polyformer)."""
+        if score_basis is not None or self.group_dim != 1 or x.dim() != 4:
+            _unsupported("LearnedSoftAggregate with a separate score basis / group_dim != 1")
+        y = ops.soft_aggregate(x, self.feat2score.weight, self.feat2score.bias)
+        return y.unsqueeze(1) if self.keepdim else y
+
 
 class ExpandedFeatTrans(nn.Module):
     """Value projection into M modes, P.V, then (FFN) shared mid Linear + GELU, per-mode output Linear, LayerNorm
@@ -232,14 +240,15 @@ class ExpandedFeatTrans(nn.Module):
         """The expansion block whose P.V / mid / output chain hangs off one autograd node (ops.squeeze_out_fused)."""
         return self.has_FFN and isinstance(self.output, MMPrivateOutput) and isinstance(self.intermediate, MMSharedMid)
 
-    def _value_bank(self, input_feat):
-        """V' = (x Wv^T) Wm^T, the value bank already pushed through MMSharedMid's Linear (see forward)."""
+    def _value_bank(self, input_feat, tag="big"):
+        """V' = (x Wv^T) Wm^T, the value bank already pushed through MMSharedMid's Linear (see forward).  tag: precision
+        class of the bank's projections (ops.small_tag of bank rows vs. query rows)."""
         M, mid = self.num_modes, self.intermediate
         B, U2 = input_feat.shape[0], input_feat.shape[1]
         if self._can_fold():
-            return ops.folded_value_bank(input_feat, self.first_linear.weight, mid.shared_linear.weight, M)
-        v = ops.linear(input_feat, self.first_linear.weight, self.first_linear.bias)     # [B,U2,M*F]
-        return ops.linear(v.view(B, U2, M, self.feat_dim), mid.shared_linear.weight).view(B, U2, M * self.feat_dim)
+            return ops.folded_value_bank(input_feat, self.first_linear.weight, mid.shared_linear.weight, M, tag)
+        v = ops.linear(input_feat, self.first_linear.weight, self.first_linear.bias, tag=tag)     # [B,U2,M*F]
+        return ops.linear(v.view(B, U2, M, self.feat_dim), mid.shared_linear.weight, tag=tag).view(B, U2, M * self.feat_dim)
 
     def _norm_aggregate(self, y):
         p = self.output.dropout.p if self.training else 0.0
@@ -252,7 +261,7 @@ class ExpandedFeatTrans(nn.Module):
         """Fused attention entry: q [Bq,U1,M*d], k [B,U2,M*d] (projected, TF32-rounded) instead of the probabilities —
         scores, clamp, softmax and attention dropout run inside ops.squeeze_out_fused (csrc/sx_attn.cu)."""
         mid = self.intermediate
-        vp = self._value_bank(input_feat)
+        vp = self._value_bank(input_feat, ops.small_tag(input_feat.shape[1], q.shape[1]))
         p = mid.dropout.p if self.training else 0.0
         gl = self.output.group_linear
         dev = vp.device
@@ -268,10 +277,11 @@ class ExpandedFeatTrans(nn.Module):
         if not folded:
             v = ops.linear(input_feat, self.first_linear.weight, self.first_linear.bias)     # [B,U2,M*F]
         if not self.has_FFN:
-            if M != 1:
-                _unsupported("the no-FFN branch with more than one mode (Polyformer)")
             u = ops.attn_pv(attention_probs, v, M)                                           # [B,M,U1,F]
-            return ops.layer_norm(u[:, 0], self.first_norm_layer.weight, self.first_norm_layer.bias)
+            # (:453) soft-aggregate over the modes — the identity for one mode, whose feat2score then gets no gradient,
+            # exactly as in the reference — then first_norm_layer (:456)
+            z = u[:, 0] if M == 1 else self.feat_softaggr(u)
+            return ops.layer_norm(z, self.first_norm_layer.weight, self.first_norm_layer.bias)
         if folded:
             # (P V) Wm^T = P (V Wm^T): push the value bank (U2 rows) through the shared mid Linear instead of the
             # fused tokens (U1 rows), and fuse MMSharedMid's bias + GELU + dropout into the P.V epilogue.  U itself
@@ -279,7 +289,7 @@ class ExpandedFeatTrans(nn.Module):
             # With a bias-free value projection the two Linears on the bank fold into one weight-space product
             # W'_m = Wm Wv_m (batch-independent), so the bank is projected once.
             mid = self.intermediate
-            vp = self._value_bank(input_feat)
+            vp = self._value_bank(input_feat, ops.small_tag(input_feat.shape[1], attention_probs.shape[2]))
             p = mid.dropout.p if self.training else 0.0
             # ... and MMPrivateOutput's grouped Linear rides in the same autograd node (its backward fuses GELU' and
             # the dropout mask into the dG GEMM epilogue)
@@ -367,9 +377,11 @@ class CrossAttFeatTrans(nn.Module):
         if in_key is None:
             in_key = in_query
         M = self.num_modes
-        # precision classes: a projection of at most num_attractors rows is "small", a token-row projection "proj"
-        tq = "small" if in_query.shape[1] <= self.config.num_attractors else "proj"
-        tk = "small" if in_key.shape[1] <= self.config.num_attractors else "proj"
+        # precision classes (ops.small_tag): the projection of the shorter side is an attractor-row product when that side is
+        # at most a quarter of the other one; everything else is a token-row projection
+        nq, nk = in_query.shape[1], in_key.shape[1]
+        tq = ops.small_tag(nq, nk) if nq < nk else "proj"
+        tk = ops.small_tag(nk, nq) if nk < nq else "proj"
         q = ops.linear(in_query, self.query.weight, self.query.bias, tag=tq)
         k = ops.linear(in_key, self.key.weight, self.key.bias, tag=tk)
         dev = q.device
@@ -432,9 +444,10 @@ class SqueezedAttFeatTrans(nn.Module):
         so the [N x C x C] key and value GEMMs become [A x C x C] ones; exact up to fp rounding."""
         t = self.in_ator_trans
         C = self.in_feat_dim
-        x3 = ops.rt_for("small") == 0         # the attractor-row chain runs as 3-pass products: keep q1 unrounded for it
-        q1 = ops.linear(self.attractors, t.query.weight, t.query.bias, tag="small", round_out=not x3)   # [1,A,C]
-        qw = ops.linear(q1, t.key.weight.t(), tag="small")                            # Q1 Wk            [1,A,C]
+        st = ops.small_tag(self.num_attractors, in_feat.shape[1])
+        x3 = ops.rt_for(st) == 0              # the attractor-row chain runs as 3-pass products: keep q1 unrounded for it
+        q1 = ops.linear(self.attractors, t.query.weight, t.query.bias, tag=st, round_out=not x3)   # [1,A,C]
+        qw = ops.linear(q1, t.key.weight.t(), tag=st)                                 # Q1 Wk            [1,A,C]
         rb = None
         if t.key.bias is not None:                                                    # (Q1 . bk) / sqrt(C)  [A]
             rb = ops.scale(ops.matvec(q1[0], t.key.bias), 1.0 / math.sqrt(C))
@@ -450,10 +463,9 @@ class SqueezedAttFeatTrans(nn.Module):
             t.call_count += 1
         u = ops.attn_pv(probs, in_feat, 1, tag="insq", round_out=not x3)               # P1 h            [B,1,A,C]
         ot = t.out_trans
-        z = ops.linear(u[:, 0], ot.first_linear.weight, tag="small", round_out=False)  # (P1 h) Wv^T     [B,A,C]
-        # the updated attractors feed the squeeze-out key projection and the value bank: both "small"
-        return ops.layer_norm(z, ot.first_norm_layer.weight, ot.first_norm_layer.bias, consumer_tag="small",
-                              producer_tag="small")
+        z = ops.linear(u[:, 0], ot.first_linear.weight, tag=st, round_out=False)       # (P1 h) Wv^T     [B,A,C]
+        # the updated attractors feed the squeeze-out key projection and the value bank (same precision class)
+        return ops.layer_norm(z, ot.first_norm_layer.weight, ot.first_norm_layer.bias, consumer_tag=st)
 
     def forward(self, in_feat, pos_biases=None):
         if pos_biases is not None:
@@ -480,6 +492,12 @@ class LearnedSinuPosEmbedder(nn.Module):
             _unsupported("LearnedSinuPosEmbedder with omega != 1 or affine")
         self.pos_fc = nn.Linear(pos_dim, pos_embed_dim, bias=True)
         self.pos_mix_norm_layer = nn.LayerNorm(pos_embed_dim, eps=1e-12, elementwise_affine=affine)
+
+    def forward(self, pos_normed):
+        """pos_normed [..., pd] (already divided by its maximum, as SegtranPosEncoder does) -> [..., C] (reference :989-998)."""
+        shp = pos_normed.shape
+        pe = ops.pos_code(pos_normed.reshape(-1, shp[-1]), self.pos_fc.weight, self.pos_fc.bias, normalize=False)
+        return pe.view(*shp[:-1], -1)
 
 
 class SegtranPosEncoder(nn.Module):

@@ -19,6 +19,10 @@ from . import _lib as L
 # ------------------------------------------------------------------------------------------------
 # "tf32":   activations/weights stay fp32 in HBM, tensor cores consume them as TF32 (operands pre-rounded
 #           to nearest so the hardware truncation is exact) with fp32 accumulation — parity-grade (<=1e-3).
+# "bf16":   fast, NON-parity mode (BASELINE.json's "bf16 in, fp32 accum"; cfg 5): every contraction runs on the tensor
+#           cores as kind::f16 with bf16 operands (2x the TF32 rate) and fp32 accumulation; tensors stay fp32 in HBM and
+#           each GEMM operand is converted once (the bf16 copy is cached for its other uses in the step).  Statistics
+#           (LayerNorm, softmax, GELU, aggregation), the head and the optimiser stay fp32.  Error budget: DESIGN §2.
 # "tf32x3": validation mode.  No producer rounds; every GEMM runs as three TF32 passes on the split operands
 #           (A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32 accumulate), which recovers fp32-level products (~1e-6).
 #           3x the tensor work plus the operand splits — used by the parity tests to show that the kernels and
@@ -28,9 +32,10 @@ _PRECISION = "tf32"
 
 def set_precision(p: str):
     global _PRECISION
-    if p not in ("tf32", "tf32x3"):
-        raise ValueError("unsupported precision %r (this build implements 'tf32' and 'tf32x3')" % (p,))
+    if p not in ("tf32", "tf32x3", "bf16"):
+        raise ValueError("unsupported precision %r (this build implements 'tf32', 'tf32x3' and 'bf16')" % (p,))
     _PRECISION = p
+    _bf16_cache.clear()
 
 
 def get_precision() -> str:
@@ -39,15 +44,27 @@ def get_precision() -> str:
 
 # Per-contraction precision policy of the default ("tf32") mode.  Every GEMM call site carries a tag:
 #   "small": attractor-row and weight-space products (A rows or none: q1, Q1.Wk, the in-squeeze value projection, the
-#            squeeze-out key projection, the folded value bank W' = Wm Wv and V' = a W'^T) — a few % of the FLOPs;
+#            squeeze-out key projection, the folded value bank W' = Wm Wv and V' = a W'^T) — a few % of the FLOPs when
+#            the attractor bank is small against the token count ("smallwide" otherwise, see small_tag);
 #   "proj" : token-row projections (N rows x C x C: the squeeze-out query projection);
 #   "insq" : the in-squeeze attention products (A x N x C);
 #   "big"  : scores, P.V', the grouped output Linear and everything in backward that is their size.
-# A tag mapped to "tf32x3" runs as three TF32 passes on hi/lo operand splits (fp32-grade products); "tf32" is one
-# pass on TF32-rounded operands.  The default keeps the small contractions exact — they feed every token through the
-# attractor bank, so their rounding error is shared by all outputs — at no measurable cost; set_precision_policy(
-# proj="tf32x3") buys another ~30 % error reduction at the wide 2-D configs for ~1.3x their step time.
-_POLICY = {"small": "tf32x3", "proj": "tf32", "insq": "tf32", "big": "tf32"}
+# A tag mapped to "tf32x3" runs its FORWARD product as one launch over K-concatenated hi/lo operand splits (three TF32
+# partial products, fp32-grade result); "tf32" is one pass on TF32-rounded operands; backward products are always single
+# pass (gradients are held to 3e-3, not 1e-3).  The default keeps the small forward contractions exact: they feed every
+# token through the attractor bank, so their rounding error is shared by all outputs — measured at full size
+# (profiles/r2_precision_policy.txt): forward max-rel error 0.67-1.12e-3 -> 0.45-0.68e-3 on configs 1-3, while making the
+# token-row projections or the in-squeeze products 3-pass as well changes nothing.
+_POLICY = {"small": "tf32x3", "smallwide": "tf32", "proj": "tf32", "insq": "tf32", "big": "tf32"}
+
+
+def small_tag(rows_small: int, rows_tokens: int) -> str:
+    """Precision class of an attractor-row / weight-space contraction: "small" (3-pass by default) while the attractor bank
+    is at most a quarter of the token count — there its products are a few % of the layer's FLOPs (every 2-D BASELINE
+    config: 256 attractors against 1296-5184 tokens) — and "smallwide" (single pass by default) when the bank is comparable
+    to the token count (cfg 4/5: 1024 / 2048 attractors against 2744 / 5832 tokens, where these products are ~20 % of the
+    FLOPs and the single-pass error is 4-7e-4 anyway)."""
+    return "small" if 4 * int(rows_small) <= int(rows_tokens) else "smallwide"
 
 
 def set_precision_policy(**kw):
@@ -160,6 +177,7 @@ def advance_seed(device):
     """Bump the base seed once per training step (captured into CUDA graphs like any other kernel)."""
     L.call("sx_seed_advance", _base_seed(device).data_ptr(), 0xD1B54A32D192ED03, _stream())
     _begin_zero_arena(device)                   # step boundary: one memset for all zero-initialised scratch of the step
+    _bf16_cache.clear()
 
 
 def new_dropout_seed(device) -> torch.Tensor:
@@ -266,6 +284,32 @@ def _as4(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+# bf16 operand copies of the current step (precision "bf16"): key -> (source tensor kept alive, bf16 copy).  Holding the
+# source keeps its storage from being recycled under a live key; the cache is emptied at every step boundary.
+_bf16_cache = {}
+_BF16_CACHE_MAX = 96
+
+
+def _bf16_view(t4: torch.Tensor) -> torch.Tensor:
+    """fp32 4-D operand view -> bf16 tensor with the same logical layout (element strides), converted once per step."""
+    key = (t4.data_ptr(), tuple(t4.shape), tuple(t4.stride()), t4._version)
+    hit = _bf16_cache.get(key)
+    if hit is not None:
+        return hit[1]
+    dims = sorted(((st, sz) for st, sz in zip(t4.stride(), t4.shape) if sz > 1), key=lambda x: x[0])
+    dense, span = True, 1
+    for st, sz in dims:
+        dense = dense and st == span
+        span *= sz
+    src = t4 if dense else t4.contiguous()
+    out = torch.empty_strided(src.size(), src.stride(), device=src.device, dtype=torch.bfloat16)
+    L.call("sx_convert", src.data_ptr(), L.SX_F32, src.numel(), out.data_ptr(), L.SX_BF16, 0, _stream())
+    if len(_bf16_cache) >= _BF16_CACHE_MAX:
+        _bf16_cache.pop(next(iter(_bf16_cache)))
+    _bf16_cache[key] = (t4, out)
+    return out
+
+
 def _pick_split_k(M, N, K, Z, bk=32, sms=148, epi=10):
     """Split-K factor for a GEMM whose tile count does not fill the machine: minimise
     rounds(tiles*sk / SMs) * (k-blocks per unit + epilogue cost in k-block units)."""
@@ -287,8 +331,7 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
                preact: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: Optional[int] = None,
                amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
                reduce_z1: bool = False, addend: Optional[torch.Tensor] = None,
-               gelu_bwd: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
-               rowdot=None, softmax_bwd=None) -> torch.Tensor:
+               gelu_bwd: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a [..., M, K], b [..., N, K] (strided fp32 views; either dim may be the contiguous one) ->
     out [z1, z0, M, N] fp32.  With reduce_z1 the z1 batch dim is summed into one output (atomic accumulate)."""
     _req_cuda(a, b, out, bias, preact, amax)
@@ -306,8 +349,7 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
             raise L.SxError("gemm_nt: batch dims do not broadcast")
     oz1 = 1 if reduce_z1 else Z1
     fresh = out is None
-    linear_epi = (not gelu) and preact is None and drop_p == 0.0 and amax is None and gelu_bwd is None and \
-        softmax_bwd is None
+    linear_epi = (not gelu) and preact is None and drop_p == 0.0 and amax is None and gelu_bwd is None
     if split_k is None:
         split_k = _pick_split_k(M, N, K, Z0 * Z1) if (linear_epi and (fresh or accumulate or reduce_z1)) else 1
     if fresh:
@@ -320,6 +362,9 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
         raise L.SxError("gemm_nt: bad output view %s %s" % (tuple(o4.shape), o4.stride()))
     g = L.sx_gemm_args()
     g.op_dtype = L.SX_OP_TF32
+    if _PRECISION == "bf16":
+        a4, b4 = _bf16_view(a4), _bf16_view(b4)
+        g.op_dtype = L.SX_OP_BF16
     g.M, g.N, g.K, g.Z0, g.Z1 = M, N, K, Z0, Z1
     g.A = _operand(a4, Z1, Z0, "A")
     g.B = _operand(b4, Z1, Z0, "B")
@@ -363,20 +408,6 @@ def _gemm_nt_1(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] 
         if addend.dtype != torch.float32 or tuple(addend.shape[-2:]) != (M, N) or _as4(addend).stride() != o4.stride():
             raise L.SxError("gemm_nt: addend must be an fp32 tensor in the output's layout")
         g.addend = addend.data_ptr()
-    if rowdot is not None:                   # (D [Z1,Z0,M] accumulated into, sub [N] or None): see SX_ACT_GELU_BWD / rowdot
-        D, sub = rowdot
-        if gelu_bwd is None or D.numel() != Z1 * Z0 * M or not D.is_contiguous():
-            raise L.SxError("gemm_nt: rowdot needs gelu_bwd and a contiguous [Z1,Z0,M] accumulator")
-        g.rowdot = D.data_ptr()
-        g.rowdot_sub = _ptr(sub)
-    if softmax_bwd is not None:              # (S raw scores in the output's layout, lse [Z1,Z0,M], D [Z1,Z0,M], clip)
-        Sx, lse, D, clip = softmax_bwd
-        if gelu or gelu_bwd is not None or preact is not None or _as4(Sx).stride() != o4.stride() or \
-                lse.numel() != Z1 * Z0 * M or D.numel() != Z1 * Z0 * M:
-            raise L.SxError("gemm_nt: softmax_bwd needs the scores in the output's layout and per-row lse / dot vectors")
-        g.act = L.SX_ACT_SOFTMAX_BWD
-        g.preact = Sx.data_ptr()
-        g.row_lse, g.row_dot, g.clip = lse.data_ptr(), D.data_ptr(), float(clip)
     L.call("sx_gemm", C.byref(g), _stream())
     if round_after and fresh:                # (caller-provided accumulators are gradient buffers: never rounded)
         L.call("sx_convert", out.data_ptr(), L.SX_F32, out.numel(), out.data_ptr(), L.SX_F32, 1, _stream())
@@ -389,22 +420,20 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, out: Optional[torch.Tensor] = N
             amax: Optional[torch.Tensor] = None, drop_p: float = 0.0, seed: int = 0, round_out: bool = True,
             reduce_z1: bool = False, gelu_bwd: Optional[torch.Tensor] = None,
             addend: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
-            rowdot=None, softmax_bwd=None, tag: str = "big") -> torch.Tensor:
+            tag: str = "big") -> torch.Tensor:
     """C[..., m, n] = epilogue(alpha * sum_k a[..., m, k] b[..., n, k]) on the tcgen05 GEMM.  One launch on TF32-rounded
     operands, or — in 'tf32x3' mode / for call-site classes the precision policy maps to it — three passes on the hi/lo
     operand splits (fp32-grade products)."""
     if not _three_pass(tag):
         return _gemm_nt_1(a, b, out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu, preact=preact,
                           accumulate=accumulate, split_k=split_k, amax=amax, drop_p=drop_p, seed=seed,
-                          round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd, addend=addend, colsum=colsum,
-                          rowdot=rowdot, softmax_bwd=softmax_bwd)
+                          round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd, addend=addend, colsum=colsum)
     _req_cuda(a, b)
     # ONE launch over K-concatenated operand splits: [A_hi | A_lo | A_hi] . [B_hi | B_hi | B_lo]^T (fp32 accumulation in TMEM
     # over the three partial products), so every epilogue / accumulate / split-K option works unchanged
     return _gemm_nt_1(_split_cat(a, 0), _split_cat(b, 1), out=out, alpha=alpha, bias=bias, bias_mode=bias_mode, gelu=gelu,
                       preact=preact, accumulate=accumulate, split_k=split_k, amax=amax, drop_p=drop_p, seed=seed,
-                      round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd, addend=addend, colsum=colsum,
-                      rowdot=rowdot, softmax_bwd=softmax_bwd)
+                      round_out=round_out, reduce_z1=reduce_z1, gelu_bwd=gelu_bwd, addend=addend, colsum=colsum)
 
 
 def _split_cat(t: torch.Tensor, role: int) -> torch.Tensor:
@@ -502,22 +531,24 @@ class _Linear(torch.autograd.Function):
     def backward(ctx, dy):
         x2, Wr, h = ctx.saved_tensors
         shp, has_b, gelu, drop_p, seed, tag = ctx.meta
+        W, b = ctx.leaves
+        if _three_pass(tag) and _PRECISION == "tf32":       # 3-pass forward, single-pass backward: TF32-rounded weight
+            Wr = round_tf32(W)
         dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
         if gelu:
             dh = torch.empty_like(dy2)
             L.call("sx_gelu_bwd", dy2.data_ptr(), h.data_ptr(), L.SX_F32, dy2.numel(), drop_p, *_seed_args(seed), dh.data_ptr(),
-                   L.SX_F32, rt_for(tag), _stream())
+                   L.SX_F32, _rt(), _stream())
             dy2 = dh
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
-            dx = gemm_nt(dy2, Wr.t(), round_out=False, tag=tag).view(shp)
-        W, b = ctx.leaves
+            dx = gemm_nt(dy2, Wr.t(), round_out=False).view(shp)
         if ctx.needs_input_grad[1]:
             tgt = _grad_target(W)
             if tgt is not None:
-                gemm_nt(dy2.t(), x2.t(), out=tgt, accumulate=True, round_out=False, tag=tag)
+                gemm_nt(dy2.t(), x2.t(), out=tgt, accumulate=True, round_out=False)
             else:
-                dW = gemm_nt(dy2.t(), x2.t(), round_out=False, tag=tag).view(Wr.shape)
+                dW = gemm_nt(dy2.t(), x2.t(), round_out=False).view(Wr.shape)
         if has_b and ctx.needs_input_grad[2]:
             tgt = _grad_target(b)
             if tgt is not None:
@@ -599,7 +630,7 @@ def attn_probs_fused(q, k, M, clip=500.0, drop_p=0.0, seed=0, diag=None, need_sc
     S = _rowpad_empty((B, M, U1, U2), q.device) if need_scores else None
     lse = torch.empty((B, M, U1), device=q.device, dtype=torch.float32)
     rowmax = torch.empty((B, M, U1), device=q.device, dtype=torch.float32)
-    stat = _zeros((2,), q.device)
+    stat = _zeros((3,), q.device)
     a = L.sx_attn_probs_args()
     a.B, a.M, a.U1, a.U2, a.d = B, M, U1, U2, d
     a.round_tf32 = 1 if (round_out and _PRECISION == "tf32") else 0
@@ -794,18 +825,20 @@ class _FoldedValueBank(torch.autograd.Function):
     folded into ONE weight-space product (M F^2 C MACs, batch-independent) and ONE projection of the A attractor rows."""
 
     @staticmethod
-    def forward(ctx, a, Wv, Wm, M):
+    def forward(ctx, a, Wv, Wm, M, tag):
         B, A, Cd = a.shape
         Fd = Wm.shape[0]
         a2 = a.reshape(B * A, Cd)
         if not a2.is_contiguous():
             a2 = a2.contiguous()
-        x3 = _three_pass("small")
+        x3 = _three_pass(tag)
         Wvr = (Wv.contiguous() if x3 else round_tf32(Wv)).view(M, 1, Fd, Cd)      # [m, f, c]
         Wmr = Wm.contiguous() if x3 else round_tf32(Wm)                           # [o, f]
         # W'_m = Wm Wv_m [M,1,F(o),C]: kept unrounded when the bank projection below runs as a 3-pass product
-        Wf = gemm_nt(Wmr.view(1, 1, Fd, Fd), Wvr.transpose(-1, -2), tag="small", round_out=not x3)
-        Vp = gemm_nt(a2, Wf.view(M * Fd, Cd), tag="small")[0, 0]      # [B*A, M*F], TF32-rounded: the P.V' operand
+        Wf = gemm_nt(Wmr.view(1, 1, Fd, Fd), Wvr.transpose(-1, -2), tag=tag, round_out=not x3)
+        Vp = gemm_nt(a2, Wf.view(M * Fd, Cd), tag=tag)[0, 0]      # [B*A, M*F], TF32-rounded: the P.V' operand
+        if x3 and _PRECISION == "tf32":                               # single-pass backward: TF32-rounded operands
+            Wf, Wvr, Wmr = round_tf32(Wf), round_tf32(Wv).view(M, 1, Fd, Cd), round_tf32(Wm)
         ctx.save_for_backward(a2, Wf, Wvr, Wmr)
         ctx.meta = (B, A, Cd, Fd, M, Wv.shape)
         ctx.leaves = (Wv, Wm)
@@ -821,27 +854,27 @@ class _FoldedValueBank(torch.autograd.Function):
             d2 = d2.contiguous()
         da = dWv = dWm = None
         if ctx.needs_input_grad[0]:
-            da = gemm_nt(d2, Wf.view(M * Fd, Cd).t(), round_out=False, tag="small")[0, 0].view(B, A, Cd)
+            da = gemm_nt(d2, Wf.view(M * Fd, Cd).t(), round_out=False)[0, 0].view(B, A, Cd)
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            dWf = gemm_nt(d2.t(), a2.t(), round_out=False, tag="small").view(M, 1, Fd, Cd)          # [m, o, c]
+            dWf = gemm_nt(d2.t(), a2.t(), round_out=False).view(M, 1, Fd, Cd)          # [m, o, c]
             if ctx.needs_input_grad[2]:                               # dWm[o,f] = sum_m dW'_m[o,:] . Wv_m[f,:]
                 tgt = _grad_target(Wm)
                 if tgt is not None:
-                    gemm_nt(dWf, Wvr, out=tgt.view(1, 1, Fd, Fd), reduce_z1=True, accumulate=True, round_out=False, tag="small")
+                    gemm_nt(dWf, Wvr, out=tgt.view(1, 1, Fd, Fd), reduce_z1=True, accumulate=True, round_out=False)
                 else:
-                    dWm = gemm_nt(dWf, Wvr, reduce_z1=True, round_out=False, tag="small").view(Fd, Fd)
+                    dWm = gemm_nt(dWf, Wvr, reduce_z1=True, round_out=False).view(Fd, Fd)
             if ctx.needs_input_grad[1]:                               # dWv_m[f,c] = sum_o Wm[o,f] dW'_m[o,c]
                 tgt = _grad_target(Wv)
                 if tgt is not None:
                     gemm_nt(Wmr.t().view(1, 1, Fd, Fd), dWf.transpose(-1, -2), out=tgt.view(M, 1, Fd, Cd), accumulate=True,
-                            round_out=False, tag="small")
+                            round_out=False)
                 else:
-                    dWv = gemm_nt(Wmr.t().view(1, 1, Fd, Fd), dWf.transpose(-1, -2), round_out=False, tag="small").view(wv_shape)
-        return da, dWv, dWm, None
+                    dWv = gemm_nt(Wmr.t().view(1, 1, Fd, Fd), dWf.transpose(-1, -2), round_out=False).view(wv_shape)
+        return da, dWv, dWm, None, None
 
 
-def folded_value_bank(a, Wv, Wm, M):
-    return _FoldedValueBank.apply(a, Wv, Wm, M)
+def folded_value_bank(a, Wv, Wm, M, tag="small"):
+    return _FoldedValueBank.apply(a, Wv, Wm, M, tag)
 
 
 def attn_pv_gelu(P, v, M, bias, drop_p=0.0, seed=0):
@@ -935,9 +968,12 @@ class _SqueezeOutFused(torch.autograd.Function):
     (:447, :243-245, :267) as ONE autograd node:
       forward : sx_attn_probs_fwd (tcgen05 scores -> in-TMEM softmax -> P)  ->  P.V' GEMM (bias/GELU/dropout epilogue)
                 -> grouped output Linear;
-      backward: dH GEMM (GELU'/dropout epilogue; it also accumulates the softmax row term D = sum_f dU_f U_f and the
-                bias-gradient column sums) -> dS GEMM (dP = dH V'^T with the softmax backward in its epilogue: P is
-                recomputed from the saved raw scores, dP never exists in memory) -> dV', dQ, dK, dWo, dbo products."""
+      backward: dH GEMM (GELU'/dropout epilogue + bias-gradient column sums) -> dP GEMM -> sx_softmax_bwd on the saved raw
+                scores (P recomputed from S and the row log-sum-exp, the row term sum_a P_a dP_a taken from the SAME dP values
+                it is subtracted from) -> dV', dQ, dK, dWo, dbo products.
+    A flash-attention style backward (row term from sum_f dU_f U_f in the dH epilogue, softmax backward in the dP GEMM
+    epilogue) was built and measured: its row term carries independent TF32 rounding, which the softmax Jacobian amplifies
+    (input-gradient error 1.3e-2 at cfg 1 / cfg 4 against 6e-4 for this form), so it is not used."""
 
     @staticmethod
     def forward(ctx, q, k, vp, M, clip, att_p, att_seed, bm, hid_p, hid_seed, Wo, bo, diag):
@@ -947,7 +983,7 @@ class _SqueezeOutFused(torch.autograd.Function):
         q = q.contiguous()
         k = k.contiguous()
         need_bwd = any(ctx.needs_input_grad)
-        P, S, lse, _rowmax, _stat = attn_probs_fused(q, k, M, clip, att_p, att_seed, diag, need_scores=need_bwd)
+        P, S, lse, _rowmax, stat = attn_probs_fused(q, k, M, clip, att_p, att_seed, diag, need_scores=need_bwd)
         vv = vp.view(B, U2, M, Fd).permute(0, 2, 3, 1)
         G = torch.empty((B, M, U1, Fd), device=P.device, dtype=torch.float32)
         H = torch.empty_like(G)
@@ -955,7 +991,7 @@ class _SqueezeOutFused(torch.autograd.Function):
         Wr = round_tf32(Wo).reshape(M, Fd, Fd)
         Y = torch.empty_like(G)
         gemm_nt(G, Wr.unsqueeze(0), out=Y, bias=bo.reshape(1, M, Fd), round_out=False)
-        ctx.save_for_backward(q, k, P, S, lse, vp, H, G, Wr)
+        ctx.save_for_backward(q, k, P, S, lse, stat, vp, H, G, Wr)
         ctx.meta = (M, Fd, float(clip), att_p, hid_p, bm is not None, Wo.shape)
         ctx.seeds = (att_seed, hid_seed)
         ctx.leaves = (bm, Wo, bo)
@@ -963,7 +999,7 @@ class _SqueezeOutFused(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dY):
-        q, k, P, S, lse, vp, H, G, Wr = ctx.saved_tensors
+        q, k, P, S, lse, stat, vp, H, G, Wr = ctx.saved_tensors
         M, Fd, clip, att_p, hid_p, has_bm, wshape = ctx.meta
         att_seed, hid_seed = ctx.seeds
         bm, Wo, bo = ctx.leaves
@@ -971,18 +1007,14 @@ class _SqueezeOutFused(torch.autograd.Function):
         Bq, d = q.shape[0], q.shape[-1] // M
         dY = dY.contiguous()
         dq = dk = dvp = dbm = dW = dbo = None
-        # dH = mask * (dY Wo) * gelu'(H); the same epilogue accumulates D[b,m,n] = sum_f dH U (U = H - bm = P V') and the
-        # column sums of dH (MMSharedMid's bias gradient)
+        # dH = mask * (dY Wo) * gelu'(H); the same epilogue accumulates the column sums of dH (MMSharedMid's bias gradient)
         dH = torch.empty_like(H)
         dbm_buf = None
         if has_bm and ctx.needs_input_grad[7]:
             tgt = _grad_target(bm)
             dbm_buf = tgt if tgt is not None else _zeros((Fd,), dY.device)
             dbm = None if tgt is not None else dbm_buf
-        need_ds = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        D = _zeros((B, M, U1), dY.device) if need_ds else None
-        gemm_nt(dY, Wr.transpose(-1, -2).unsqueeze(0), out=dH, gelu_bwd=H, drop_p=hid_p, seed=hid_seed, colsum=dbm_buf,
-                rowdot=None if D is None else (D, bm))
+        gemm_nt(dY, Wr.transpose(-1, -2).unsqueeze(0), out=dH, gelu_bwd=H, drop_p=hid_p, seed=hid_seed, colsum=dbm_buf)
         if ctx.needs_input_grad[10]:
             tgt = _grad_target(Wo)
             if tgt is not None:
@@ -999,11 +1031,13 @@ class _SqueezeOutFused(torch.autograd.Function):
             dvp = torch.empty_like(vp)
             gemm_nt(P.transpose(-1, -2), dH.transpose(-1, -2), out=dvp.view(B, U2, M, Fd).permute(0, 2, 1, 3),
                     round_out=False)
-        if need_ds:
-            # dS = P * (mask_att * dPd - D) with dPd = dH V'^T never written: the softmax backward is the GEMM's epilogue
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dP = torch.empty_strided(P.size(), P.stride(), device=P.device, dtype=torch.float32)
+            gemm_nt(dH, vp.view(B, U2, M, Fd).permute(0, 2, 1, 3), out=dP, round_out=False)
             dS = torch.empty_strided(P.size(), P.stride(), device=P.device, dtype=torch.float32)
-            gemm_nt(dH, vp.view(B, U2, M, Fd).permute(0, 2, 1, 3), out=dS, drop_p=att_p, seed=att_seed,
-                    softmax_bwd=(S, lse, D, clip))
+            ld = P.stride(-2)
+            L.call("sx_softmax_bwd", dP.data_ptr(), ld, S.data_ptr(), ld, lse.data_ptr(), B * M * U1, U2,
+                   stat[2:].data_ptr(), clip, att_p, *_seed_args(att_seed), ld, dS.data_ptr(), L.SX_F32, ld, _rt(), _stream())
             scale = 1.0 / math.sqrt(d)
             if ctx.needs_input_grad[0]:
                 bcast = Bq == 1 and B > 1
@@ -1127,16 +1161,56 @@ class _LnSoftAggr(torch.autograd.Function):
         return dY, dg, db, dws, dbs, None, None
 
 
+class _SoftAggr(torch.autograd.Function):
+    """out = sum_m softmax_m(x_m . ws + bs) x_m  — LearnedSoftAggregate (segtran_shared.py:318-325) without a LayerNorm in
+    front: the no-FFN branch of ExpandedFeatTrans (:453) with M modes, i.e. the Polyformer layer.  x [B,M,N,F] -> [B,N,F]."""
+
+    @staticmethod
+    def forward(ctx, x, ws, bs):
+        x = x.contiguous()
+        B, M, N, Fd = x.shape
+        wsc, bsc = ws.contiguous().view(-1), bs.contiguous().view(-1)
+        out = torch.empty((B, N, Fd), device=x.device, dtype=torch.float32)
+        wts = torch.empty((B, M, N), device=x.device, dtype=torch.float32)
+        L.call("sx_softaggr_fwd", x.data_ptr(), B, M, N, Fd, wsc.data_ptr(), bsc.data_ptr(), out.data_ptr(), wts.data_ptr(),
+               _stream())
+        ctx.save_for_backward(x, wsc, wts)
+        ctx.shapes = (ws.shape, bs.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, wsc, wts = ctx.saved_tensors
+        B, M, N, Fd = x.shape
+        dout = dout.contiguous()
+        dx = torch.empty_like(x)
+        dscore = torch.empty((B, M, N), device=x.device, dtype=torch.float32)
+        L.call("sx_softaggr_bwd", dout.data_ptr(), x.data_ptr(), B, M, N, Fd, wsc.data_ptr(), wts.data_ptr(), dx.data_ptr(),
+               dscore.data_ptr(), _stream())
+        R = B * M * N
+        dws = _sgemm(dscore, x, 1, Fd, R, (1, 1), (Fd, 1))[0].view(ctx.shapes[0])         # sum_r dscore[r] x[r,:]
+        dbs = _zeros((1,), x.device)
+        L.call("sx_rowsum", dscore.data_ptr(), 1, R, R, 1, dbs.data_ptr(), _stream())
+        return dx, dws, dbs.view(ctx.shapes[1])
+
+
+def soft_aggregate(x, ws, bs):
+    return _SoftAggr.apply(x, ws, bs)
+
+
 class _PosCode(torch.autograd.Function):
     """LearnedSinuPosEmbedder (segtran_shared.py:989-998) on pos/pos.max() (:1231): [R,pd] -> [R,C0]."""
 
     @staticmethod
-    def forward(ctx, pos2d, W, b):
+    def forward(ctx, pos2d, W, b, normalize):
         pos2d = pos2d.contiguous().float()
         R, pd = pos2d.shape
         C0 = W.shape[0]
-        pmax = torch.empty(1, device=pos2d.device, dtype=torch.float32)
-        L.call("sx_reduce_max", pos2d.data_ptr(), pos2d.numel(), pmax.data_ptr(), _stream())
+        if normalize:
+            pmax = torch.empty(1, device=pos2d.device, dtype=torch.float32)
+            L.call("sx_reduce_max", pos2d.data_ptr(), pos2d.numel(), pmax.data_ptr(), _stream())
+        else:
+            pmax = torch.ones(1, device=pos2d.device, dtype=torch.float32)
         pe = torch.empty((R, C0), device=pos2d.device, dtype=torch.float32)
         Wc, bc = W.contiguous(), b.contiguous()
         L.call("sx_pos_lsinu_fwd", pos2d.data_ptr(), pmax.data_ptr(), R, pd, Wc.data_ptr(), bc.data_ptr(), C0,
@@ -1156,7 +1230,7 @@ class _PosCode(torch.autograd.Function):
         dbb, db = _sink_or_zeros(ctx.leaves[1], like=b)
         L.call("sx_pos_lsinu_bwd", pos2d.data_ptr(), pmax.data_ptr(), R, pd, W.data_ptr(), b.data_ptr(), C0,
                dpe.data_ptr(), scratch.data_ptr(), dWb.data_ptr(), dbb.data_ptr(), _stream())
-        return None, dW, db
+        return None, dW, db, None
 
 
 class _Prologue(torch.autograd.Function):
@@ -1265,8 +1339,9 @@ def ln_softaggr(Y, g, b, ws, bs, drop_p=0.0, seed=0):
     return _LnSoftAggr.apply(Y, g, b, ws, bs, drop_p, seed)
 
 
-def pos_code(pos2d, W, b):
-    return _PosCode.apply(pos2d, W, b)
+def pos_code(pos2d, W, b, normalize=True):
+    """normalize: divide the positions by their global maximum first (SegtranPosEncoder.forward, :1231)."""
+    return _PosCode.apply(pos2d, W, b, bool(normalize))
 
 
 def prologue(x, g, b, pe, posw, mask, drop_p=0.0, seed=0):

@@ -63,3 +63,15 @@ def build_b200_encoder(fx, device="cuda", dropout=0.0):
     enc.apply(init.tie_qk)
     enc.load_state_dict(fx["state_dict"], strict=True)
     return enc.to(device)
+
+
+class AffinePickNet(torch.nn.Module):
+    """Stand-in segmentation net for the inference-path fixtures: class k's score = a[k] * x[:, ch[k]] + b[k] — element-wise, so
+    it is reproducible to the last ulp on any device (the sliding-window logic is what the fixtures pin, not a network)."""
+
+    def __init__(self, a, b, ch):
+        super().__init__()
+        self.a, self.b, self.ch = [float(v) for v in a], [float(v) for v in b], [int(c) for c in ch]
+
+    def forward(self, x):
+        return torch.stack([x[:, c] * a + b for a, b, c in zip(self.a, self.b, self.ch)], dim=1)
