@@ -693,7 +693,17 @@ def run_b200(args):
             for k, v in timer.gemm_shapes().items():
                 print("GEMM %-40s %8.3f ms %8.1f TF/s x%d" % (k, v["ms"], v["tflops"], v["n"]), file=sys.stderr)
     if world > 1:
-        dist.destroy_process_group()
+        # a CUDA graph that captured NCCL work keeps the communicator busy: destroy_process_group() then never returns
+        # (observed: both ranks stuck there after the result line was printed).  Drop the graph, drain the device, make sure
+        # every rank got here, and leave without the collective teardown.
+        compute_fn = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -713,6 +723,10 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce of the whole bucket after the step")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
+    wd = float(os.environ.get("SEGTRAN_BENCH_WATCHDOG_S", "0"))
+    if wd > 0:                                     # debugging aid: dump every thread's Python stack and exit if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -49,6 +49,18 @@ def _worker(rank, world, port, q):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", device_id=dev)
     try:
+        _worker_body(rank, dev, dist, q)
+    except Exception:                                        # report instead of leaving the peer stuck in a collective
+        import traceback
+        q.put((rank, "error", traceback.format_exc()[-1500:], False))
+    torch.cuda.synchronize()
+    q.close()
+    q.join_thread()
+    os._exit(0)                                              # (no collective teardown: it can block on in-flight NCCL state)
+
+
+def _worker_body(rank, dev, dist, q):
+    if True:
         import bench
         import segtran_b200.networks.segtran_shared as S
         from segtran_b200 import ops
@@ -81,8 +93,6 @@ def _worker(rank, world, port, q):
         torch.cuda.synchronize()
         err = float((grads - flat).abs().max() / flat.abs().max())
         q.put((rank, same_params, err, early == len(bucket.params)))
-    finally:
-        dist.destroy_process_group()
 
 
 def hp_ref_unique(ps):
@@ -103,7 +113,13 @@ def test_two_gpu_dp_step_matches_single_gpu_and_ranks_agree():
     ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in ps:
         p.start()
-    res = [q.get(timeout=300) for _ in ps]
+    res = []
+    for _ in ps:
+        res.append(q.get(timeout=240))
+        if res[-1][1] == "error":
+            for p in ps:
+                p.kill()
+            raise AssertionError("rank %d failed:\n%s" % (res[-1][0], res[-1][2]))
     for p in ps:
         p.join(timeout=60)
     print("2-GPU DP:", res)
