@@ -606,9 +606,9 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
   const int sms = sm_count_cached();
   SX_REQUIRE(sms > 0, "sx_gemm: no CUDA device (this library has no CPU fallback)");
 
-  // CTA-pair kernel (TF32 only): automatic for shapes with at least one full wave of 256-row tiles
+  // CTA-pair kernel: automatic for shapes with at least one full wave of 256-row tiles
   bool cg2 = false;
-  if (es == 4 && g_knobs.cg2 != 0 && sms >= 2) {
+  if (g_knobs.cg2 != 0 && sms >= 2) {
     if (g_knobs.cg2 > 0) {
       cg2 = true;
     } else if (a->M > BM) {
@@ -709,6 +709,11 @@ extern "C" int sx_gemm(const sx_gemm_args* a, void* stream) {
     if (!amn && bmn) return launch<4, false, true, false>(ta, tb, tc, tp, p, grid, st);
     if (amn && !bmn) return launch<4, true, false, false>(ta, tb, tc, tp, p, grid, st);
     return launch<4, true, true, false>(ta, tb, tc, tp, p, grid, st);
+  } else if (cg2) {
+    if (!amn && !bmn) return launch<2, false, false, true>(ta, tb, tc, tp, p, grid, st);
+    if (!amn && bmn) return launch<2, false, true, true>(ta, tb, tc, tp, p, grid, st);
+    if (amn && !bmn) return launch<2, true, false, true>(ta, tb, tc, tp, p, grid, st);
+    return launch<2, true, true, true>(ta, tb, tc, tp, p, grid, st);
   } else {
     if (!amn && !bmn) return launch<2, false, false, false>(ta, tb, tc, tp, p, grid, st);
     if (!amn && bmn) return launch<2, false, true, false>(ta, tb, tc, tp, p, grid, st);

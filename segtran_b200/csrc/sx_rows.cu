@@ -2,6 +2,8 @@
 // LayerNorm + learned soft-aggregation over modes, GELU backward, casts and column reductions.
 // One warp owns one row; rows are staged once in shared memory and re-read from there, so every
 // tensor is read from HBM exactly once and written once.  All statistics are fp32.
+#include <algorithm>
+
 #include "sx_common.cuh"
 
 namespace {
@@ -507,6 +509,7 @@ __global__ void ln_softaggr_bwd_kernel(const float* __restrict__ dout, const flo
 }
 
 #include "sx_rows_fast.cuh"
+#include "sx_rows_cta.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // elementwise helpers
@@ -1064,6 +1067,20 @@ extern "C" int sx_ln_softaggr_fwd(const float* Y, int32_t B, int32_t M, int32_t 
                                   const float* b, const float* ws, const float* bs, float drop_p, uint64_t seed, const uint64_t* seed_dev,
                                   float* out, float* stats, float* wts, void* stream) {
   SX_REQUIRE(M >= 1 && M <= MAX_MODES, "sx_ln_softaggr_fwd: num_modes %d not in 1..%d", M, MAX_MODES);
+  if (F % 4 == 0 && F <= 2048 && (M == 1 || M == 2 || M == 4) && al16(Y) && al16(out) && al16(g) && al16(b) && al16(ws)) {
+    // CTA-per-token kernel: every mode row of a token in registers, Y read once
+    const long long T = (long long)B * N;
+    const int grid = (int)std::min<long long>(T, (long long)sms_cached() * (F <= 1024 ? 4 : 2));
+#define SX_LAUNCH(NV_, MM_, TT_)                                                                                        \
+  ln_softaggr_fwd_cta<NV_, MM_, TT_><<<grid, TT_, 0, ST(stream)>>>(Y, B, N, F, g, b, ws, bs, drop_p, seed,              \
+                                                                    (const unsigned long long*)seed_dev, out, stats, wts)
+#define SX_MODES(NV_, TT_) do { if (M == 4) SX_LAUNCH(NV_, 4, TT_); else if (M == 2) SX_LAUNCH(NV_, 2, TT_); else SX_LAUNCH(NV_, 1, TT_); } while (0)
+    if (F <= 512) SX_MODES(1, 128); else if (F <= 1024) SX_MODES(2, 128); else SX_MODES(2, 256);
+#undef SX_MODES
+#undef SX_LAUNCH
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (F % 4 == 0 && nv_for(F) && al16(Y) && al16(out) && al16(g) && al16(b) && al16(ws)) {
     const int grid = grid_for_rows((long long)B * N, FAST_WARPS, sms_cached() * 2);
 #define SX_LAUNCH(NV_)                                                                                          \
@@ -1091,6 +1108,22 @@ extern "C" int sx_ln_softaggr_bwd(const float* dout, const float* Y, int32_t B, 
                                   const float* stats, const float* wts, void* dY, int32_t dy_dtype, int32_t round_tf32,
                                   float* dg, float* db, float* dws, float* dbs, float* dscore_scratch, void* stream) {
   SX_REQUIRE(M >= 1 && M <= MAX_MODES, "sx_ln_softaggr_bwd: num_modes %d not in 1..%d", M, MAX_MODES);
+  if (dy_dtype == SX_F32 && F % 4 == 0 && F <= 2048 && (M == 1 || M == 2 || M == 4) && al16(Y) && al16(dout) && al16(dY) &&
+      al16(g) && al16(b) && al16(ws)) {
+    // CTA-per-token kernel: Y and dout read once, dY written once, column gradients accumulated in registers
+    const long long T = (long long)B * N;
+    const int grid = (int)std::min<long long>(T, (long long)sms_cached() * (F <= 1024 ? 3 : 2));
+#define SX_LAUNCH(NV_, MM_, TT_)                                                                                        \
+  ln_softaggr_bwd_cta<NV_, MM_, TT_><<<grid, TT_, 0, ST(stream)>>>(dout, Y, B, N, F, g, b, ws, drop_p, seed,            \
+                                                                    (const unsigned long long*)seed_dev, stats, wts,    \
+                                                                    (float*)dY, round_tf32, dg, db, dws, dbs)
+#define SX_MODES(NV_, TT_) do { if (M == 4) SX_LAUNCH(NV_, 4, TT_); else if (M == 2) SX_LAUNCH(NV_, 2, TT_); else SX_LAUNCH(NV_, 1, TT_); } while (0)
+    if (F <= 512) SX_MODES(1, 128); else if (F <= 1024) SX_MODES(2, 128); else SX_MODES(2, 256);
+#undef SX_MODES
+#undef SX_LAUNCH
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (dy_dtype == SX_F32 && dscore_scratch && F % 4 == 0 && nv_for(F) && al16(Y) && al16(dout) && al16(dY) && al16(g) &&
       al16(b) && al16(ws)) {
     const int grid = grid_for_rows((long long)B * N, FAST_WARPS, sms_cached() * 2);

@@ -291,16 +291,32 @@ _BF16_CACHE_MAX = 96
 
 
 def _bf16_view(t4: torch.Tensor) -> torch.Tensor:
-    """fp32 4-D operand view -> bf16 tensor with the same logical layout (element strides), converted once per step."""
+    """fp32 4-D operand view -> bf16 tensor with the same logical layout (element strides), converted once per step.
+    The conversion is done on the view's whole underlying storage (one pass, shared by every other view of the same
+    tensor: q/k/v mode slices, transposes, the forward and the backward uses); storages much larger than the view
+    (slices of an arena) are converted per view."""
+    st = t4.untyped_storage()
+    n_st = st.nbytes() // 4
+    if n_st <= 4 * t4.numel() + 1024 and st.data_ptr() % 16 == 0:
+        key = ("st", st.data_ptr(), n_st, t4._version)
+        hit = _bf16_cache.get(key)
+        if hit is None:
+            flat = torch.empty(n_st, device=t4.device, dtype=torch.bfloat16)
+            L.call("sx_convert", st.data_ptr(), L.SX_F32, n_st, flat.data_ptr(), L.SX_BF16, 0, _stream())
+            if len(_bf16_cache) >= _BF16_CACHE_MAX:
+                _bf16_cache.pop(next(iter(_bf16_cache)))
+            hit = (t4, flat)
+            _bf16_cache[key] = hit
+        return torch.as_strided(hit[1], t4.size(), t4.stride(), t4.storage_offset())
     key = (t4.data_ptr(), tuple(t4.shape), tuple(t4.stride()), t4._version)
     hit = _bf16_cache.get(key)
     if hit is not None:
         return hit[1]
-    dims = sorted(((st, sz) for st, sz in zip(t4.stride(), t4.shape) if sz > 1), key=lambda x: x[0])
+    dims = sorted(((s_, z_) for s_, z_ in zip(t4.stride(), t4.shape) if z_ > 1), key=lambda x: x[0])
     dense, span = True, 1
-    for st, sz in dims:
-        dense = dense and st == span
-        span *= sz
+    for s_, z_ in dims:
+        dense = dense and s_ == span
+        span *= z_
     src = t4 if dense else t4.contiguous()
     out = torch.empty_strided(src.size(), src.stride(), device=src.device, dtype=torch.bfloat16)
     L.call("sx_convert", src.data_ptr(), L.SX_F32, src.numel(), out.data_ptr(), L.SX_BF16, 0, _stream())
