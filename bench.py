@@ -437,6 +437,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     precision = args.precision or c["precision"]
     ops.set_precision(precision)
+    if os.environ.get("SEGTRAN_GEMM_MAX_CTAS"):            # bring-up knob: cap the persistent GEMM grids (SMs left to NCCL)
+        L.call("sx_gemm_debug_set", b"max_ctas", int(os.environ["SEGTRAN_GEMM_MAX_CTAS"]))
     if args.no_fused_attn:
         ops.set_attn_fusion(False)
     B = local_batch(c, args, world)

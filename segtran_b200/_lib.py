@@ -129,7 +129,7 @@ def check(rc, what):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
-_LAUNCHES = {"sx_pos_lsinu_bwd": 2, "sx_ln_softaggr_bwd": 2, "sx_prologue_bwd": 3, "sx_layernorm_bwd": 2, "sx_gemm_debug_set": 0,
+_LAUNCHES = {"sx_pos_lsinu_bwd": 2, "sx_ln_softaggr_bwd": 1, "sx_prologue_bwd": 2, "sx_layernorm_bwd": 2, "sx_gemm_debug_set": 0,
              "sx_attn_probs_fwd": 3}
 launch_count = 0
 _hook = None          # optional callable(name, args) -> context manager, installed by bench.py for per-kernel timing

@@ -862,6 +862,19 @@ extern "C" int sx_prologue_fwd(const float* x, int64_t B, int32_t N, int32_t C, 
                                const float* pe, int32_t C0, int64_t pe_bstride, float posw, const float* mask,
                                float drop_p, uint64_t seed, const uint64_t* seed_dev, void* h, int32_t h_dtype, int32_t round_tf32, float* stats,
                                void* stream) {
+  if (h_dtype == SX_F32 && C % 4 == 0 && C <= 2048 && C0 % 4 == 0 && pe_bstride % 4 == 0 && al16(x) && al16(h) && al16(pe) &&
+      al16(g) && al16(b)) {
+    // CTA-per-row kernel: the row in registers, 16-byte accesses at every width
+    const long long R = (long long)B * N;
+#define SX_LAUNCH(NV_, TT_)                                                                                             \
+  prologue_fwd_cta<NV_, TT_><<<(int)std::min<long long>(R, (long long)sms_cached() * (1024 / TT_)), TT_, 0, ST(stream)>>>( \
+      x, R, N, C, g, b, pe, C0, pe_bstride, posw, mask, drop_p, seed, (const unsigned long long*)seed_dev, (float*)h, stats, \
+      round_tf32)
+    if (C <= 512) SX_LAUNCH(1, 128); else if (C <= 1024) SX_LAUNCH(2, 128); else SX_LAUNCH(2, 256);
+#undef SX_LAUNCH
+    SX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t smem = (size_t)ROW_WARPS * C * 4;
   SX_REQUIRE(smem <= 200 * 1024, "sx_prologue_fwd: C=%d too large", C);
   const long long R = (long long)B * N;
@@ -883,6 +896,26 @@ extern "C" int sx_prologue_bwd(const float* dh, const float* x, int64_t B, int32
                                const float* b, const float* pe, int32_t C0, int64_t pe_bstride, float posw,
                                const float* mask, float drop_p, uint64_t seed, const uint64_t* seed_dev, const float* stats, float* dx, float* dg,
                                float* db, float* dpe, float* dt_scratch, void* stream) {
+  if (C % 4 == 0 && C <= 2048 && C0 % 4 == 0 && pe_bstride % 4 == 0 && al16(dh) && al16(x) && al16(dx) && al16(pe) && al16(g) &&
+      al16(b) && (!dpe || (dt_scratch && al16(dt_scratch) && al16(dpe)))) {
+    // CTA-per-row kernel: x / dh read once, dx (and dt, when the positional-code gradient needs it) written once, dg / db
+    // accumulated in registers
+    const long long R = (long long)B * N;
+    float* dt = dpe ? dt_scratch : nullptr;
+#define SX_LAUNCH(NV_, TT_)                                                                                             \
+  prologue_bwd_cta<NV_, TT_><<<(int)std::min<long long>(R, (long long)sms_cached() * (768 / TT_)), TT_, 0, ST(stream)>>>( \
+      dh, x, R, N, C, g, b, pe, C0, pe_bstride, posw, mask, drop_p, seed, (const unsigned long long*)seed_dev, stats, dx, dt, \
+      dg, db)
+    if (C <= 512) SX_LAUNCH(1, 128); else if (C <= 1024) SX_LAUNCH(2, 128); else SX_LAUNCH(2, 256);
+#undef SX_LAUNCH
+    SX_CHECK_CUDA(cudaGetLastError());
+    if (dpe) {
+      pos_grad_from_dt_fast<<<grid_for_rows((long long)N * (C / 4), 256, sms_cached()), 256, 0, ST(stream)>>>(
+          dt_scratch, (int)B, N, C, C0, pe_bstride, posw, dpe);
+      SX_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
   if (dt_scratch && C % 4 == 0 && C0 % 4 == 0 && pe_bstride % 4 == 0 && nv_for(C) && al16(dh) && al16(x) && al16(dx) &&
       al16(pe) && al16(g) && al16(b) && al16(dt_scratch) && (!dpe || al16(dpe))) {
     const long long R = (long long)B * N;

@@ -280,3 +280,167 @@ ln_softaggr_bwd_cta(const float* __restrict__ dout, const float* __restrict__ Y,
   }
   if (tid == 0 && dbs_acc != 0.f) atomicAdd(dbs, dbs_acc);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Fused prologue, CTA-per-row forms (segtran_shared.py:916, :930-934, :944-946):
+//   h = mask * dropout( LN( LN_{g,b}(x) + posw * pe[..., :C] ) )
+// One CTA per token row, the row in NV float4 registers per thread: x is read once and h written once with 16-byte
+// accesses at any width (the warp-per-row forward staged rows in shared memory with 4-byte accesses; the backward kept
+// 64 row registers per lane at the 2-D widths), and the backward accumulates dg / db in registers across the rows a CTA
+// visits instead of a column-parallel kernel that re-reads x and dt.
+// ------------------------------------------------------------------------------------------------
+template <int NV, int TT>
+__global__ void __launch_bounds__(TT, 1024 / TT)
+prologue_fwd_cta(const float* __restrict__ x, long long R, int N, int C, const float* __restrict__ g, const float* __restrict__ b,
+                 const float* __restrict__ pe, int C0, long long pe_bstride, float posw, const float* __restrict__ mask,
+                 float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev, float* __restrict__ h,
+                 float* __restrict__ stats, int rnd) {
+  seed += seed_dev ? *seed_dev : 0ull;
+  __shared__ float red[2 * (TT / 32)];
+  int par = 0;
+  const int tid = threadIdx.x;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const uint32_t p16 = sx::drop_p16(drop_p);
+  for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+    const long long bi = r / N, ni = r % N;
+    const float* per = pe + bi * pe_bstride + ni * C0;
+    float4 v[NV];
+    float s[1] = {0.f};
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * tid + 4 * TT * i;
+      v[i] = c < C ? *reinterpret_cast<const float4*>(x + r * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s[0] += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    cta_sum<1, TT>(s, red, par);
+    const float m1 = s[0] / C;
+    s[0] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (4 * tid + 4 * TT * i < C) {
+        v[i].x -= m1; v[i].y -= m1; v[i].z -= m1; v[i].w -= m1;
+        s[0] += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+    cta_sum<1, TT>(s, red, par);
+    const float r1 = rsqrtf(s[0] / C + LN_EPS);
+    s[0] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * tid + 4 * TT * i;
+      if (c < C) {
+        const float4 gg = ld4(g + c), bb = ld4(b + c), pp = ld4(per + c);
+        v[i].x = v[i].x * r1 * gg.x + bb.x + posw * pp.x; v[i].y = v[i].y * r1 * gg.y + bb.y + posw * pp.y;
+        v[i].z = v[i].z * r1 * gg.z + bb.z + posw * pp.z; v[i].w = v[i].w * r1 * gg.w + bb.w + posw * pp.w;
+        s[0] += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    cta_sum<1, TT>(s, red, par);
+    const float m2 = s[0] / C;
+    s[0] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (4 * tid + 4 * TT * i < C) {
+        v[i].x -= m2; v[i].y -= m2; v[i].z -= m2; v[i].w -= m2;
+        s[0] += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+    cta_sum<1, TT>(s, red, par);
+    const float r2 = rsqrtf(s[0] / C + LN_EPS);
+    const float mk = (mask ? mask[r] : 1.f) * r2;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * tid + 4 * TT * i;
+      if (c < C) {
+        float4 o = make_float4(v[i].x * mk, v[i].y * mk, v[i].z * mk, v[i].w * mk);
+        if (drop_p > 0.f) o = mask4(o, keep4(seed, (unsigned long long)(r * C + c), p16), keep_scale);
+        *reinterpret_cast<float4*>(h + r * C + c) = rnd4(o, rnd);
+      }
+    }
+    if (tid == 0) { stats[r * 4 + 0] = m1; stats[r * 4 + 1] = r1; stats[r * 4 + 2] = m2; stats[r * 4 + 3] = r2; }
+  }
+}
+
+// dx from dh; dt (the gradient at the inner LayerNorm's input, needed by the positional-code gradient) is written to
+// dt_out; dg[c] += sum_r dt * xhat1, db[c] += sum_r dt accumulated in registers, one atomicAdd per column per CTA
+template <int NV, int TT>
+__global__ void __launch_bounds__(TT, 768 / TT)
+prologue_bwd_cta(const float* __restrict__ dh, const float* __restrict__ x, long long R, int N, int C, const float* __restrict__ g,
+                 const float* __restrict__ b, const float* __restrict__ pe, int C0, long long pe_bstride, float posw,
+                 const float* __restrict__ mask, float drop_p, unsigned long long seed,
+                 const unsigned long long* __restrict__ seed_dev, const float* __restrict__ stats, float* __restrict__ dx,
+                 float* __restrict__ dt_out, float* __restrict__ dg, float* __restrict__ db) {
+  seed += seed_dev ? *seed_dev : 0ull;
+  __shared__ float red[2 * (TT / 32) * 2];
+  int par = 0;
+  const int tid = threadIdx.x;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const uint32_t p16 = sx::drop_p16(drop_p);
+  float4 ag[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+    const float m1 = stats[r * 4 + 0], r1 = stats[r * 4 + 1], m2 = stats[r * 4 + 2], r2 = stats[r * 4 + 3];
+    const long long bi = r / N, ni = r % N;
+    const float* per = pe + bi * pe_bstride + ni * C0;
+    const float mk = mask ? mask[r] : 1.f;
+    float4 a[NV], yh[NV], d[NV];
+    float s[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * tid + 4 * TT * i;
+      yh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C) {
+        a[i] = *reinterpret_cast<const float4*>(x + r * C + c);
+        d[i] = *reinterpret_cast<const float4*>(dh + r * C + c);
+        const float4 gg = ld4(g + c), bb = ld4(b + c), pp = ld4(per + c);
+        a[i].x = (a[i].x - m1) * r1; a[i].y = (a[i].y - m1) * r1; a[i].z = (a[i].z - m1) * r1; a[i].w = (a[i].w - m1) * r1;
+        yh[i].x = (a[i].x * gg.x + bb.x + posw * pp.x - m2) * r2; yh[i].y = (a[i].y * gg.y + bb.y + posw * pp.y - m2) * r2;
+        yh[i].z = (a[i].z * gg.z + bb.z + posw * pp.z - m2) * r2; yh[i].w = (a[i].w * gg.w + bb.w + posw * pp.w - m2) * r2;
+        d[i].x *= mk; d[i].y *= mk; d[i].z *= mk; d[i].w *= mk;
+        if (drop_p > 0.f) d[i] = mask4(d[i], keep4(seed, (unsigned long long)(r * C + c), p16), keep_scale);
+        s[0] += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+        s[1] += (d[i].x * yh[i].x + d[i].y * yh[i].y) + (d[i].z * yh[i].z + d[i].w * yh[i].w);
+      } else {
+        a[i] = d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    cta_sum<2, TT>(s, red, par);
+    const float s1 = s[0] / C, s2 = s[1] / C;
+    s[0] = s[1] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * tid + 4 * TT * i;
+      if (c < C) {
+        const float4 gg = ld4(g + c);
+        float4 dt;
+        dt.x = r2 * (d[i].x - s1 - yh[i].x * s2); dt.y = r2 * (d[i].y - s1 - yh[i].y * s2);
+        dt.z = r2 * (d[i].z - s1 - yh[i].z * s2); dt.w = r2 * (d[i].w - s1 - yh[i].w * s2);
+        if (dt_out) *reinterpret_cast<float4*>(dt_out + r * C + c) = dt;
+        ag[i].x += dt.x * a[i].x; ag[i].y += dt.y * a[i].y; ag[i].z += dt.z * a[i].z; ag[i].w += dt.w * a[i].w;
+        ab[i].x += dt.x; ab[i].y += dt.y; ab[i].z += dt.z; ab[i].w += dt.w;
+        d[i] = make_float4(dt.x * gg.x, dt.y * gg.y, dt.z * gg.z, dt.w * gg.w);
+        s[0] += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+        s[1] += (d[i].x * a[i].x + d[i].y * a[i].y) + (d[i].z * a[i].z + d[i].w * a[i].w);
+      }
+    }
+    cta_sum<2, TT>(s, red, par);
+    const float s3 = s[0] / C, s4 = s[1] / C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * tid + 4 * TT * i;
+      if (c < C) {
+        float4 o;
+        o.x = r1 * (d[i].x - s3 - a[i].x * s4); o.y = r1 * (d[i].y - s3 - a[i].y * s4);
+        o.z = r1 * (d[i].z - s3 - a[i].z * s4); o.w = r1 * (d[i].w - s3 - a[i].w * s4);
+        *reinterpret_cast<float4*>(dx + r * C + c) = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = 4 * tid + 4 * TT * i;
+    if (c < C) {
+      atomicAdd(dg + c, ag[i].x); atomicAdd(dg + c + 1, ag[i].y); atomicAdd(dg + c + 2, ag[i].z); atomicAdd(dg + c + 3, ag[i].w);
+      atomicAdd(db + c, ab[i].x); atomicAdd(db + c + 1, ab[i].y); atomicAdd(db + c + 2, ab[i].z); atomicAdd(db + c + 3, ab[i].w);
+    }
+  }
+}

@@ -9,7 +9,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-TINY = dict(kind="3d", title="tiny 3-D shell", backbone="tiny3d", B=2, S=16, grid=(4, 4, 4), dims=[48, 48], compress=[1, 1],
+TINY = dict(kind="3d", title="tiny 3-D shell", backbone="i3d", B=2, S=16, grid=(4, 4, 4), dims=[48, 48], compress=[1, 1],
             Cf=32, sp1=(8, 8, 8), classes=2, attractors=16, modes=4, qk_bias=True, ref_gflop=0.0, precision="tf32")
 
 
@@ -64,7 +64,7 @@ def _worker_body(rank, dev, dist, q):
         import bench
         import segtran_b200.networks.segtran_shared as S
         from segtran_b200 import ops
-        S.bb2feat_dims["tiny3d"] = [8, 16, 24, 32, 48]
+        S.bb2feat_dims["i3d"] = [8, 16, 24, 32, 48]      # (this subprocess only) tiny widths under the i3d shell
         c = TINY
         Bg = 4                                               # global batch, split 2 + 2
         g = torch.Generator().manual_seed(7)
