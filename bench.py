@@ -676,6 +676,30 @@ def run_b200(args):
                 "loss": float(hloss)}
         if checksum_agree is not None:
             line["dp_param_checksums_agree"] = checksum_agree
+        if world == 1 and precision == "tf32" and not args.no_fp32_equivalent:
+            # the same step with every contraction as an error-compensated 3-pass TF32 product (fp32-grade results,
+            # 1e-7 .. 1e-5 against the fp32 oracle): what the default mode's TF32 trade buys.  Eager launches (no graph).
+            ops.set_precision("tf32x3")
+            try:
+                for _ in range(2):
+                    compute()
+                    if opt is not None:
+                        opt.step()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                nf = max(2, min(args.steps, 5))
+                torch.cuda.synchronize()
+                f0.record()
+                for _ in range(nf):
+                    compute()
+                    if opt is not None:
+                        opt.step()
+                f1.record()
+                torch.cuda.synchronize()
+                fms = f0.elapsed_time(f1) / nf
+                line["fp32_equivalent"] = {"precision": "tf32x3", "ms_per_step": fms, "steps": nf, "launch": "eager",
+                                           "value": B * units_per_sample(c) / (fms * 1e-3), "unit": unit_name(c)}
+            finally:
+                ops.set_precision(precision)
         if world == 1 and not args.no_eager_baseline:
             compute_fn = None
             torch.cuda.empty_cache()
@@ -721,6 +745,8 @@ def main():
     ap.add_argument("--no-optimizer", action="store_true", help="leave the BertAdam update out of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--no-fp32-equivalent", action="store_true",
+                    help="skip the extra tf32x3 (fp32-grade) timing of the same step")
     ap.add_argument("--no-fused-attn", action="store_true", help="squeeze-out attention as separate GEMM + softmax kernels")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce of the whole bucket after the step")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying a CUDA graph")

@@ -1487,7 +1487,14 @@ class _HeadContract(torch.autograd.Function):
             L.call("sx_head_contract_bwd_data", dL.data_ptr(), Wcb.data_ptr(), B, Cf, V, K, dcurr.data_ptr(), _stream())
         # dWcb[k,c] = sum_{b,v} dL[b,k,v] curr[b,c,v]: a (K x Cf x B*V) product streamed once through the tensor
         # cores (TF32 operands, fp32 accumulation; HBM-bound on reading curr), reduced over the batch atomically
-        dWcb = gemm_nt(dL.view(B, 1, K, V), curr.view(B, 1, Cf, V), reduce_z1=True, round_out=False).view(K, Cf)
+        need_w = any(ctx.needs_input_grad[1:5])
+        if not need_w:
+            return dcurr, None, None, None, None, (dL.view(B, K, V) if has_tv else None)
+        if V % 4 == 0:
+            dWcb = gemm_nt(dL.view(B, 1, K, V), curr.view(B, 1, Cf, V), reduce_z1=True, round_out=False).view(K, Cf)
+        else:                                         # TMA needs 16-byte row pitches: CUDA-core reduction instead
+            dWcb = _zeros((K, Cf), curr.device)
+            L.call("sx_head_contract_bwd_weight", dL.data_ptr(), curr.data_ptr(), B, Cf, V, K, dWcb.data_ptr(), _stream())
         dcc = _zeros((K,), curr.device)               # d(const)[k] = sum_{b,v} dL
         L.call("sx_rowsum", dL.data_ptr(), B * K, V, V, K, dcc.data_ptr(), _stream())
         if Wb2 is not None:

@@ -297,3 +297,34 @@ def test_seg_head_3d_equals_uncollapsed():
     close(y, yr, 1e-4)                # forward is exact fp32 arithmetic (CUDA cores)
     for a_, b_ in zip((curr, vf, Wb, bb, Wc, bc), ts):
         close(a_.grad, b_.grad, 3e-3)  # weight gradients stream curr through the tensor cores as TF32
+
+
+def test_seg_head_2d_odd_voxel_count_and_frozen_weights():
+    """V = 7*9 is not a multiple of 4: the weight gradient takes the CUDA-core reduction (TMA needs 16-byte pitches);
+    with every weight frozen no weight-gradient kernel runs and the data gradients are unchanged."""
+    from segtran_b200 import ops
+    B, Cf, Fd, K = 2, 16, 16, 3
+    grid, sp1, out_size = (3, 4), (7, 9), (21, 27)
+    for frozen in (False, True):
+        torch.manual_seed(3)
+        curr = torch.randn(B, Cf, *sp1, device="cuda", requires_grad=True)
+        vf = torch.randn(B, 12, Fd, device="cuda", requires_grad=True)
+        Wb = torch.randn(Fd, Cf, 1, 1, device="cuda", requires_grad=not frozen)
+        bb = torch.randn(Fd, device="cuda", requires_grad=not frozen)
+        Wc = torch.randn(K, Fd, 1, 1, device="cuda", requires_grad=not frozen)
+        bc = torch.randn(K, device="cuda", requires_grad=not frozen)
+        y = ops.seg_head(curr, vf, grid, Wb, bb, Wc, bc, out_size)
+        go = torch.randn_like(y)
+        y.backward(go)
+        ts = [t.detach().clone().requires_grad_(t.requires_grad) for t in (curr, vf, Wb, bb, Wc, bc)]
+        c2, v2, Wb2, bb2, Wc2, bc2 = ts
+        up = F.interpolate(v2.transpose(1, 2).reshape(B, Fd, *grid), size=sp1, mode="bilinear", align_corners=False)
+        s = F.conv2d(F.conv2d(c2, Wb2, bb2) + up, Wc2, bc2)
+        yr = F.interpolate(s, size=out_size, mode="bilinear", align_corners=False)
+        yr.backward(go)
+        close(y, yr, 1e-4)
+        for a_, b_ in zip((curr, vf, Wb, bb, Wc, bc), ts):
+            if b_.requires_grad:
+                close(a_.grad, b_.grad, 1e-4 if frozen else 3e-3)
+            else:
+                assert a_.grad is None
