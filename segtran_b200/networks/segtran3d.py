@@ -213,7 +213,7 @@ class Segtran3d(SegtranInitWeights):
         return cur
 
     def in_fpn_forward(self, batch_base_feats, nonzero_mask):
-        """In-FPN pyramid + depth pooling (stock ops): -> feat_fpn [B,C0,D2,H2,W2], vmask [B,N]."""
+        """In-FPN pyramid + depth pooling: -> feat_fpn [B,C0,D2,H2,W2], vmask [B,N]."""
         cur = self._pyramid(batch_base_feats, self.in_fpn_layers[:-1], self.in_fpn_convs, self.in_fpn_norms,
                             self.in_fpn_scheme, self.in_fpn_layers[0])
         bc = self.in_fpn_bridgeconv
@@ -223,8 +223,12 @@ class Segtran3d(SegtranInitWeights):
             cur = bc(cur)
         size = list(cur.shape[2:])
         size[0] //= self.D_pool_K
-        cur = F.interpolate(cur, size=size, mode='trilinear', align_corners=False)
-        m = F.interpolate(nonzero_mask.float().unsqueeze(1), size=size, mode='trilinear', align_corners=False)
+        if ops.fpn_fusion_enabled():                                     # depth pooling / mask pooling: sx_resize_axis
+            cur = ops.resize_linear(cur, size)
+            m = ops.resize_linear(nonzero_mask.float().unsqueeze(1), size)
+        else:
+            cur = F.interpolate(cur, size=size, mode='trilinear', align_corners=False)
+            m = F.interpolate(nonzero_mask.float().unsqueeze(1), size=size, mode='trilinear', align_corners=False)
         vmask = (m.squeeze(1) >= 0.5).long().reshape(cur.shape[0], -1)
         return cur, vmask
 
