@@ -1,11 +1,11 @@
 #!/bin/bash
-# One bench line per BASELINE.json config on one GPU (device-timed value, e2e, roofline, PyTorch-CUDA eager baseline);
-# the CPU baseline is measured separately (run_cpu_baselines.sh) so that this stays within a few GPU-minutes.
+# One bench line per BASELINE.json config on one GPU (device-timed value, e2e, roofline, PyTorch-CUDA eager baseline, CPU
+# baseline with a 40 s budget per config so that the whole script stays within ~10 GPU-minutes).
 # usage: bash profiles/run_all_configs.sh [tag]
 tag=${1:-r2}
 mkdir -p gpurun_out
 for c in 4 1 2 3 5; do
-  timeout 400 python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_cfg${c}.json 2> gpurun_out/${tag}_cfg${c}.err || echo "cfg $c failed rc=$?"
+  SEGTRAN_CPU_BUDGET_S=40 timeout 500 python bench.py --config $c --steps 10 --warmup 3 > gpurun_out/${tag}_cfg${c}.json 2> gpurun_out/${tag}_cfg${c}.err || echo "cfg $c failed rc=$?"
 done
 for c in 4 5; do
   timeout 400 python bench.py --config $c --precision bf16 --steps 10 --warmup 3 --no-cpu-baseline --no-eager-baseline > gpurun_out/${tag}_cfg${c}_bf16.json 2> gpurun_out/${tag}_cfg${c}_bf16.err || echo "cfg $c bf16 failed rc=$?"

@@ -315,8 +315,14 @@ __device__ __forceinline__ uint32_t drop_p16(float p) {
   return v >= 65535.f ? 65535u : (uint32_t)v;
 }
 __device__ __forceinline__ uint32_t drop_mul(int w) { return w ? 0x85EBCA77u : 0x9E3779B1u; }
+// word key: a splitmix64 finalisation of the whole 64-bit seed offset by a per-word constant — both words depend on all
+// seed bits (two seeds that differ in one 32-bit half only must not share a word's mask).  Loop-invariant in every kernel.
 __device__ __forceinline__ uint32_t drop_key(unsigned long long seed, int w) {
-  return w ? ((uint32_t)(seed >> 32) ^ 0x68E31DA4u) : (uint32_t)seed;
+  unsigned long long z = seed + (w ? 0x68E31DA4A0761D65ull : 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)z ^ (uint32_t)(z >> 32);
 }
 __device__ __forceinline__ uint32_t drop_word_k(uint32_t mul, uint32_t key, unsigned long long idx4) {
   uint32_t a = ((uint32_t)idx4 * mul) ^ key;

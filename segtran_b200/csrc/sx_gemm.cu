@@ -344,6 +344,12 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     };
 
+    // dropout constants of this thread (the word key is a 64-bit mix of the seed: computed once, not per chunk)
+    const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const uint32_t drop_p16v = sx::drop_p16(p.drop_p);
+    const unsigned long long drop_seed = p.drop_p > 0.f ? p.drop_seed + (p.drop_seed_dev ? *p.drop_seed_dev : 0ull) : 0ull;
+    const uint32_t drop_mul_t = sx::drop_mul((tc >> 1) & 1), drop_key_t = sx::drop_key(drop_seed, (tc >> 1) & 1);
+
     for (int t = cid; t < p.total_tiles; t += ncl, ++it) {
       int z0, z1, mb, nb, ks;
       decode(t, z0, z1, mb, nb, ks);
@@ -402,14 +408,13 @@ sx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         auto apply_dropout = [&]() {
           if (p.drop_p > 0.f) {
-            const float keep_scale = 1.f / (1.f - p.drop_p);
-            const uint32_t p16 = sx::drop_p16(p.drop_p);
-            const unsigned long long dseed = p.drop_seed + (p.drop_seed_dev ? *p.drop_seed_dev : 0ull);
+            const float keep_scale = drop_scale;
+            const uint32_t p16 = drop_p16v;
+            const unsigned long long dseed = drop_seed;
             if (((p.ldc | zoff) & 3) == 0) {
               // rows start on a 4-element hash group: this thread's pair is always elements (tc&2, tc&2 + 1) of its
               // group, i.e. one 32-bit word per pair with a per-thread constant multiplier / key
-              const int w = (tc >> 1) & 1;
-              const uint32_t mul = sx::drop_mul(w), key = sx::drop_key(dseed, w);
+              const uint32_t mul = drop_mul_t, key = drop_key_t;
 #pragma unroll
               for (int P = 0; P < 2; ++P)
 #pragma unroll

@@ -10,6 +10,16 @@ pytestmark = pytest.mark.gpu
 P = 0.3
 
 
+@pytest.fixture(autouse=True)
+def _fp32_grade_precision():
+    """tf32x3 mode: no kernel rounds its output to TF32 for a following tensor-core operand, so kept values can be compared
+    with (no-dropout value) / (1-p) to fp32 accuracy.  The masks do not depend on the precision mode."""
+    from segtran_b200 import ops
+    ops.set_precision("tf32x3")
+    yield
+    ops.set_precision("tf32")
+
+
 def _check_mask(kept, p=P, row_tol=0.1, col_tol=0.1):
     rate = float(kept.float().mean())
     n = kept.numel()
