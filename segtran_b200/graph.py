@@ -3,7 +3,8 @@
 The stack launches ~115 kernels per step at cfg 4; enqueueing them from Python costs about as much host time as the
 GPU needs to run them.  Every kernel on the path is capture-safe (no host synchronisation, no host-side random
 numbers: dropout seeds live on the device, see ops.new_dropout_seed), so the step can be recorded once and replayed
-with a single launch.  Gradient all-reduce stays outside the graph (GradBucket) so NCCL is not captured.
+with a single launch.  At N>1 the gradient all-reduce is captured with it: GradBucket issues the NCCL calls on a side
+stream that forks from and re-joins the capturing stream (parallel.py, milestones), so they become nodes of the same graph.
 """
 from __future__ import annotations
 
