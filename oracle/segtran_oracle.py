@@ -24,7 +24,7 @@ restructure; the parity tests then prove the restructuring is value-preserving.
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence
 
 import torch
 import torch.nn.functional as F

@@ -1,6 +1,6 @@
 """Times the fused scores+softmax kernel (sx_attn_probs_fwd) alone at the squeeze-out shapes of the BASELINE configs.
 usage: python profiles/run_attn_kernel.py [cfg4|cfg2|cfg5] [iters]"""
-import os, sys, math
+import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from segtran_b200 import ops

@@ -10,7 +10,6 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 from torch.nn import Parameter
 
 from .. import ops

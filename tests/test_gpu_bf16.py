@@ -4,7 +4,7 @@ encoder fixtures forward + backward within the mode's error budget."""
 import pytest
 import torch
 
-from tests.helpers import build_b200_encoder, load_golden, rel_err
+from tests.helpers import rel_err
 
 pytestmark = pytest.mark.gpu
 

@@ -1,5 +1,4 @@
 """Per-kernel GPU tests: each segtran_b200 op against the same op written in plain PyTorch fp32 (on the GPU)."""
-import math
 
 import pytest
 import torch

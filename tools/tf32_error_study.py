@@ -4,7 +4,7 @@ Runs the oracle twice on the 2-D BASELINE stack widths: exact fp32, and with eve
 (round-to-nearest-away, fp64 accumulate), optionally keeping selected call sites exact, over several seeds.
     python tools/tf32_error_study.py
 """
-import sys, os, math
+import sys, os
 import torch
 import torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
