@@ -763,7 +763,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     wd = float(os.environ.get("SEGTRAN_BENCH_WATCHDOG_S", "0"))
-    if wd > 0:                                     # debugging aid: dump every thread's Python stack and exit if the run stalls
+    if wd == 0 and args.impl != "reference" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        wd = 900.0                                 # a multi-rank run takes ~1 min: a stalled collective must not hang the launcher
+    if wd > 0:                                     # dump every thread's Python stack and exit if the run stalls
         import faulthandler
         faulthandler.dump_traceback_later(wd, exit=True)
     if args.impl == "reference":
