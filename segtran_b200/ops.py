@@ -111,8 +111,12 @@ def set_grad_ready_callback(fn):
 
 
 def grad_ready(t: torch.Tensor, params):
-    """When backward reaches `t`, announce that the gradients of `params` are final.  No-op without a callback."""
-    if _GRAD_READY_CB is None or not isinstance(t, torch.Tensor) or not t.requires_grad:
+    """When backward reaches `t`, announce that the gradients of `params` are final.  No-op without a callback.
+    `t` must be the RESULT of an operation: its hook then runs as a pre-hook of the node that produced it, i.e. after every
+    node created later AND after their (top-priority) AccumulateGrad nodes.  A leaf's hook sits on its own AccumulateGrad
+    node, whose order against the AccumulateGrad nodes of sibling parameters is unspecified — leaves are therefore not
+    marked (their parameters are covered by the final GradBucket.allreduce_async())."""
+    if _GRAD_READY_CB is None or not isinstance(t, torch.Tensor) or not t.requires_grad or t.grad_fn is None:
         return
     ps = list(params)
     cb = _GRAD_READY_CB
